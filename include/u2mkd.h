@@ -1,0 +1,137 @@
+/*
+ * u2mkd.h — C-ABI of the B200-native (sm_100a) LiDAR point-voxel hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what the
+ * reference's native binding for this path — torchsparse v1.4.0 `torchsparse.backend`
+ * [TS v1.4.0 torchsparse/backend/pybind_cuda.cpp], pinned at
+ * /root/reference/README.md:44-48 and called from core/models/utils.py and
+ * core/models/build_blocks.py through torchsparse.nn.functional — would bind instead.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes; no torch / C++ types.
+ *   - every pointer is DEVICE memory owned by the caller unless stated otherwise;
+ *     the library never allocates: scratch is caller-provided, its size queried first.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and
+ *     re-entrant; no global mutable state besides the thread-local error string.
+ *   - returns 0 on success, non-zero on error; u2_last_error() explains (thread-local).
+ *   - coordinates are int32 [N,4] rows (x, y, z, batch) — batch LAST
+ *     (core/models/semantickitti/spvcnn.py:90, core/models/utils.py:17).
+ *   - "miss" sentinel is -1 everywhere (core/models/utils.py:97-98).
+ */
+#ifndef U2MKD_H_
+#define U2MKD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *u2_stream_t; /* cudaStream_t */
+
+/* arithmetic modes of the conv GEMMs */
+enum {
+    U2_MATH_FP32 = 0, /* FFMA, fp32-exact parity mode (rel 1e-4 bar)             */
+    U2_MATH_TF32 = 1, /* tcgen05 kind::tf32, fp32 storage (rel 2e-2 bar)          */
+    U2_MATH_BF16 = 2  /* tcgen05 kind::f16 on bf16-rounded operands (rel 2e-2 bar) */
+};
+
+const char *u2_last_error(void);
+int u2_version(void);
+/* 1 if the library was built with the tcgen05 (TF32/BF16) conv kernels */
+int u2_has_tensor_core_path(void);
+
+/* ---- hashing: replaces backend.hash_cuda / backend.kernel_hash_cuda
+ * [TS backend/hash/hash_cuda.cu]; callers core/models/utils.py:19,43,49,86,92.
+ * offsets == NULL: out[n].  else offsets int32 [K,3]: out[K,n] = hash(x+ox, y+oy, z+oz, b). */
+int u2_hash(const int32_t *coords, int64_t n, const int32_t *offsets, int32_t K, int64_t *out,
+            u2_stream_t stream);
+
+/* ---- hash table: replaces backend.hash_query_cuda
+ * [TS backend/others/query_cuda.cu + backend/hashmap/hashmap_cuda.cu];
+ * callers core/models/utils.py:21,50,93,135 through spf.sphashquery.
+ * Open addressing, 16-byte slots {int64 key, uint32 value}, capacity = pow2 >= 2*n_keys.
+ * Duplicate keys keep the SMALLEST index (== the CPU backend's "first insert wins").
+ * Key 0xFFFFFFFFFFFFFFFF is reserved (never produced by u2_hash: hashes are 60-bit). */
+size_t u2_hash_table_bytes(int64_t n_keys);
+int u2_hash_table_build(const int64_t *keys, int64_t n_keys, void *table, size_t table_bytes,
+                        u2_stream_t stream);
+/* out[i] = index of queries[i] among keys, or -1 */
+int u2_hash_table_query(const void *table, size_t table_bytes, const int64_t *queries, int64_t nq,
+                        int64_t *out, u2_stream_t stream);
+
+/* ---- count: replaces backend.count_cuda [TS backend/others/count_cuda.cu];
+ * core/models/utils.py:22,51.  out int32 [n_out] = histogram of idx[i] in [0,n_out). */
+int u2_count(const int32_t *idx, int64_t n, int32_t *out, int64_t n_out, u2_stream_t stream);
+
+/* ---- voxelize (scatter-mean): replaces backend.voxelize_{forward,backward}_cuda
+ * [TS backend/voxelize/voxelize_cuda.cu]; core/models/utils.py:24,26,58.
+ * fwd: out[n_vox,C] = mean over points i with idx[i]==v of feats[i,:]  (idx<0 dropped)
+ * bwd: gfeats[i,:] = gout[idx[i],:] / counts[idx[i]]   (0 for dropped points)        */
+int u2_voxelize_fwd(const float *feats, int64_t n_pts, int32_t C, const int32_t *idx,
+                    const int32_t *counts, float *out, int64_t n_vox, u2_stream_t stream);
+int u2_voxelize_bwd(const float *gout, int64_t n_vox, int32_t C, const int32_t *idx,
+                    const int32_t *counts, float *gfeats, int64_t n_pts, u2_stream_t stream);
+
+/* ---- trilinear weights: replaces the ~20 torch kernels of spf.calc_ti_weights
+ * [TS nn/functional/devoxelize.py]; core/models/utils.py:94-95.
+ * coords fp32 [n_pts,4]; idx_kn int64 [8,n_pts]; writes weights fp32 [8,n_pts] (same
+ * layout as the reference returns).                                                   */
+int u2_ti_weights(const float *coords, const int64_t *idx_kn, int64_t n_pts, float scale,
+                  float *weights_kn, u2_stream_t stream);
+
+/* ---- devoxelize: replaces backend.devoxelize_{forward,backward}_cuda
+ * [TS backend/devoxelize/devoxelize_cuda.cu]; core/models/utils.py:99,111.
+ * fwd: out[i,:] = sum_k w[i,k] * feats[idx[i,k],:]   (idx<0 skipped); idx int32 [n_pts,8]
+ * bwd: gfeats[idx[i,k],:] += w[i,k] * gout[i,:]      (gfeats zeroed by the call)       */
+int u2_devoxelize_fwd(const float *feats, int64_t n_vox, int32_t C, const int32_t *idx,
+                      const float *w, int64_t n_pts, float *out, u2_stream_t stream);
+int u2_devoxelize_bwd(const float *gout, int64_t n_pts, int32_t C, const int32_t *idx,
+                      const float *w, float *gfeats, int64_t n_vox, u2_stream_t stream);
+
+/* ---- strided-conv output coordinates: replaces F.spdownsample
+ * [TS nn/functional/downsample.py] for the stride in {1, kernel_size} case used by every
+ * U2MKD strided conv (core/models/build_blocks.py:25-29 with ks=2, stride=2):
+ * out = unique rows of (floor(c / s) * s, b), sorted by (b, x, y, z).
+ * n_out_dev: device int64 scalar; out_coords has room for n rows. scratch from
+ * u2_downsample_scratch_bytes(n).  Requires 0 <= x,y,z < 2^18 and 0 <= b < 2^10.       */
+size_t u2_downsample_scratch_bytes(int64_t n);
+int u2_downsample_coords(const int32_t *coords, int64_t n, int32_t sx, int32_t sy, int32_t sz,
+                         int32_t *out_coords, int64_t *n_out_dev, void *scratch,
+                         size_t scratch_bytes, u2_stream_t stream);
+
+/* ---- kernel map: replaces the sphash / sphashquery / nonzero sequence inside F.conv3d
+ * [TS nn/functional/conv.py]; SURVEY.md §3.3.
+ * nbr  int32 [K, ld_out]: nbr[k][o]  = input row i with coord(i) == coord(o)+offset_k, else -1
+ * nbrT int32 [K, ld_in ]: nbrT[k][i] = output row o of that same pair, else -1
+ * nbsizes int32 [K]      : pairs per offset (device)
+ * scratch: u2_hash_table_bytes(n_in) + 8*n_in bytes.                                    */
+size_t u2_kmap_scratch_bytes(int64_t n_in);
+int u2_kmap_build(const int32_t *in_coords, int64_t n_in, const int32_t *out_coords,
+                  int64_t n_out, const int32_t *offsets, int32_t K, int32_t *nbr, int64_t ld_out,
+                  int32_t *nbrT, int64_t ld_in, int32_t *nbsizes, void *scratch,
+                  size_t scratch_bytes, u2_stream_t stream);
+/* ---- sparse convolution: replaces backend.convolution_{forward,backward}_cuda
+ * [TS backend/convolution/convolution_cuda.cu]; core/models/build_blocks.py:25-77.
+ * One fused gather-GEMM kernel, output-stationary over the neighbour table:
+ *   Y[r,:] = sum_k X[table[k][r],:] @ Wk        Wk = W[k] (Cs x Cd)       if !w_transposed
+ *                                               Wk = W[k]^T, W [K,Cd,Cs]   if  w_transposed
+ * forward (not transposed): table = nbr,  X = input,  W = kernel
+ * forward (transposed conv): table = nbrT, X = input,  W = kernel
+ * dgrad: the other table, X = grad_out, w_transposed = 1.
+ * scratch: u2_conv_scratch_bytes(...) (0 allowed for FP32 mode).                         */
+size_t u2_conv_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math);
+int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
+                const int32_t *table, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
+                int32_t math, void *scratch, size_t scratch_bytes, u2_stream_t stream);
+/* wgrad: dW[k] (Cs x Cd) = sum_r X[table[k][r],:]^T (outer) dY[r,:], with the same table the
+ * forward used (nbr for a regular conv, nbrT for a transposed one). dW is zeroed by the call. */
+int u2_conv_wgrad(const float *X, int64_t n_src, int32_t Cs, const float *dY, int64_t n_dst,
+                  int32_t Cd, const int32_t *table, int64_t ld, int32_t K, float *dW,
+                  int32_t math, void *scratch, size_t scratch_bytes, u2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* U2MKD_H_ */

@@ -1,0 +1,282 @@
+"""Parity of the CUDA path (through the C-ABI library) against the CPU oracle, same seeded
+inputs.  Integer / index results must be bit-exact; fp32 values within rel 1e-4 measured
+as max|a-b| / max(max|b|, eps) per tensor (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL = 1e-4
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)) if a.numel() else 0.0
+
+
+def rand_coords(rng, n, extent=40, batch=2, unique=True):
+    c = rng.integers(0, extent, size=(n, 3))
+    b = rng.integers(0, batch, size=(n, 1))
+    c = np.concatenate([c, b], 1).astype(np.int32)
+    if unique:
+        c = np.unique(c, axis=0)
+        rng.shuffle(c)
+    return torch.from_numpy(np.ascontiguousarray(c))
+
+
+@pytest.fixture(scope="module")
+def gpu(cuda_lib):
+    from u2mkd_b200 import ops
+    from u2mkd_b200.torchsparse.nn import functional as F
+    ops.set_math("fp32")
+    return F
+
+
+# ---------------------------------------------------------------- hashing / query / count
+@pytest.mark.parametrize("n", [0, 1, 257, 20000])
+def test_sphash_bit_exact(gpu, oracle, n):
+    rng = np.random.default_rng(n)
+    c = torch.from_numpy(rng.integers(-50, 3000, size=(n, 4)).astype(np.int32))
+    assert torch.equal(gpu.sphash(c.cuda()).cpu(), oracle.sphash(c))
+    for ks, st in ((3, 1), (2, 4), (3, 8)):
+        off = oracle.get_kernel_offsets(ks, st)
+        assert torch.equal(gpu.sphash(c.cuda(), off.cuda()).cpu(), oracle.sphash(c, off))
+
+
+@pytest.mark.parametrize("n_ref,n_q", [(1, 5), (1000, 0), (5000, 20000), (200000, 500000)])
+def test_sphashquery_bit_exact(gpu, oracle, n_ref, n_q):
+    rng = np.random.default_rng(n_ref + n_q)
+    ref = torch.from_numpy(rng.integers(0, 2 ** 59, size=n_ref))
+    ref[n_ref // 2:] = ref[:n_ref - n_ref // 2]  # duplicates: the first occurrence must win
+    pick = torch.from_numpy(rng.integers(0, n_ref, size=n_q))
+    q = ref[pick].clone()
+    miss = torch.from_numpy(rng.random(n_q) < 0.4)
+    q[miss] = torch.from_numpy(rng.integers(0, 2 ** 59, size=int(miss.sum())))
+    q = q.view(-1, 5) if n_q % 5 == 0 and n_q else q
+    got = gpu.sphashquery(q.cuda(), ref.cuda()).cpu()
+    want = oracle.sphashquery(q, ref)
+    assert got.shape == want.shape and torch.equal(got, want)
+
+
+def test_spcount_bit_exact(gpu, oracle):
+    rng = np.random.default_rng(3)
+    idx = torch.from_numpy(rng.integers(-1, 700, size=50000).astype(np.int32))
+    assert torch.equal(gpu.spcount(idx.cuda(), 700).cpu(), oracle.spcount(idx, 700))
+    assert gpu.spcount(idx[:0].cuda(), 5).tolist() == [0] * 5
+
+
+# ---------------------------------------------------------------- voxelize / devoxelize
+@pytest.mark.parametrize("n,s,c", [(1000, 37, 4), (30000, 4000, 64), (30000, 500, 48), (5000, 100, 7), (4000, 50, 512)])
+def test_spvoxelize_fwd_bwd(gpu, oracle, n, s, c):
+    rng = np.random.default_rng(n + c)
+    idx = np.sort(rng.integers(-1, s, size=n)).astype(np.int32)
+    idx[rng.random(n) < 0.2] = rng.integers(0, s, size=1)  # break the runs
+    idx = torch.from_numpy(idx)
+    feats = torch.from_numpy(rng.standard_normal((n, c)).astype(np.float32))
+    counts = oracle.spcount(idx, s)
+    fo = feats.clone().requires_grad_(True)
+    fg = feats.clone().cuda().requires_grad_(True)
+    yo = oracle.spvoxelize(fo, idx, counts)
+    yg = gpu.spvoxelize(fg, idx.cuda(), counts.cuda())
+    assert rel_err(yg, yo) < FP32_REL
+    g = torch.from_numpy(rng.standard_normal(yo.shape).astype(np.float32))
+    yo.backward(g)
+    yg.backward(g.cuda())
+    assert rel_err(fg.grad, fo.grad) < FP32_REL
+
+
+def _devox_inputs(oracle, rng, n_vox_side, n_pts, stride, batch=2):
+    """voxels on a thinned lattice at `stride`, points at random float positions."""
+    g = np.stack(np.meshgrid(*[np.arange(n_vox_side)] * 3, indexing="ij"), -1).reshape(-1, 3) * stride
+    keep = rng.random(g.shape[0]) < 0.6
+    vox = []
+    for b in range(batch):
+        vox.append(np.concatenate([g[keep], np.full((keep.sum(), 1), b)], 1))
+    vox = torch.from_numpy(np.concatenate(vox).astype(np.int32))
+    pts = rng.random((n_pts, 3)) * (n_vox_side - 1) * stride
+    pts = np.concatenate([pts, rng.integers(0, batch, size=(n_pts, 1))], 1).astype(np.float32)
+    return vox, torch.from_numpy(pts)
+
+
+@pytest.mark.parametrize("stride,c", [(1, 16), (4, 64), (16, 256), (2, 6)])
+def test_voxel_to_point_chain(gpu, oracle, stride, c):
+    """sphash(8 offsets) -> sphashquery -> calc_ti_weights -> spdevoxelize (utils.py:84-99)."""
+    rng = np.random.default_rng(stride * 100 + c)
+    vox, pts = _devox_inputs(oracle, rng, 12, 20000, stride)
+    feats = torch.from_numpy(rng.standard_normal((vox.shape[0], c)).astype(np.float32))
+    key = torch.cat([torch.floor(pts[:, :3] / stride).int() * stride, pts[:, -1].int().view(-1, 1)], 1)
+    off = oracle.get_kernel_offsets(2, stride, 1)
+
+    idx_o = oracle.sphashquery(oracle.sphash(key, off), oracle.sphash(vox))
+    idx_g = gpu.sphashquery(gpu.sphash(key.cuda(), off.cuda()), gpu.sphash(vox.cuda()))
+    assert torch.equal(idx_g.cpu(), idx_o)
+    w_o = oracle.calc_ti_weights(pts, idx_o, scale=stride)
+    w_g = gpu.calc_ti_weights(pts.cuda(), idx_g, scale=stride)
+    assert rel_err(w_g, w_o) < 1e-6
+    idx_o, w_o = idx_o.t().contiguous(), w_o.t().contiguous()
+    idx_g, w_g = idx_g.t().contiguous(), w_g.t().contiguous()
+
+    fo = feats.clone().requires_grad_(True)
+    fg = feats.clone().cuda().requires_grad_(True)
+    yo = oracle.spdevoxelize(fo, idx_o, w_o)
+    yg = gpu.spdevoxelize(fg, idx_g, w_g)
+    assert rel_err(yg, yo) < FP32_REL
+    g = torch.from_numpy(rng.standard_normal(yo.shape).astype(np.float32))
+    yo.backward(g)
+    yg.backward(g.cuda())
+    assert rel_err(fg.grad, fo.grad) < FP32_REL
+
+
+# ---------------------------------------------------------------- kernel maps
+@pytest.mark.parametrize("ts_stride", [1, 2, 8])
+def test_spdownsample_bit_exact(gpu, oracle, ts_stride):
+    rng = np.random.default_rng(ts_stride)
+    c = rand_coords(rng, 30000, extent=60)
+    c[:, :3] *= ts_stride
+    got = gpu.spdownsample(c.cuda(), 2, 2, ts_stride).cpu()
+    want = oracle.spdownsample(c, 2, 2, ts_stride)
+    assert torch.equal(got, want)
+
+
+def test_spdownsample_general_case(gpu, oracle):
+    rng = np.random.default_rng(5)
+    c = rand_coords(rng, 3000, extent=20)
+    got = gpu.spdownsample(c.cuda(), 2, 3, 1).cpu()
+    want = oracle.spdownsample(c, 2, 3, 1)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("ks,stride,ts_stride,n", [(3, 1, 1, 20000), (3, 1, 4, 3000), (2, 2, 1, 20000), (2, 2, 2, 5000),
+                                                  (3, 1, 1, 1), (3, 1, 1, 130)])
+def test_kernel_map_bit_exact(gpu, oracle, ks, stride, ts_stride, n):
+    """nbmaps [M,2] (in,out) ordered by (k,out), nbsizes and out coords identical to the oracle's."""
+    from u2mkd_b200 import ops
+    rng = np.random.default_rng(ks * 7 + stride + n)
+    c = rand_coords(rng, n, extent=30)
+    c[:, :3] *= ts_stride
+    tstr, kst, sst = (ts_stride,) * 3, (ks,) * 3, (stride,) * 3
+    kmap_o, out_o = oracle.build_kernel_map(c, tstr, kst, sst, (1, 1, 1))
+    off = oracle.get_kernel_offsets(kst, stride=tstr)
+    cg = c.cuda()
+    out_g = gpu.spdownsample(cg, sst, kst, tstr) if stride > 1 else cg
+    assert torch.equal(out_g.cpu(), out_o)
+    km = ops.build_kernel_map(cg, out_g, off.cuda())
+    assert torch.equal(km[1].cpu().long(), kmap_o[1].long())
+    assert km[2] == kmap_o[2]
+    assert torch.equal(km[0].cpu(), kmap_o[0])
+    # transposed table is the exact inverse relation
+    K = off.shape[0]
+    nbrT = km.nbrT[:, :km.n_in].cpu()
+    pairs = set()
+    for k in range(K):
+        i = torch.nonzero(nbrT[k] >= 0).view(-1)
+        pairs.update((k, int(a), int(b)) for a, b in zip(i.tolist(), nbrT[k][i].tolist()))
+    cur = 0
+    want = set()
+    for k, m in enumerate(kmap_o[1].tolist()):
+        want.update((k, int(a), int(b)) for a, b in kmap_o[0][cur:cur + m].tolist())
+        cur += m
+    assert pairs == want
+
+
+# ---------------------------------------------------------------- convolution
+def _conv_case(oracle, gpu_ts, rng, n, cin, cout, ks, stride, extent=24, math="fp32"):
+    from u2mkd_b200 import ops
+    ops.set_math(math)
+    c = rand_coords(rng, n, extent=extent)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32))
+    conv_o = oracle.Conv3d(cin, cout, ks, stride)
+    conv_g = gpu_ts.nn.Conv3d(cin, cout, ks, stride)
+    conv_g.load_state_dict(conv_o.state_dict())
+    conv_g.cuda()
+    fo = f.clone().requires_grad_(True)
+    fg = f.clone().cuda().requires_grad_(True)
+    xo = oracle.SparseTensor(fo, c)
+    xg = gpu_ts.SparseTensor(fg, c.cuda())
+    return conv_o, conv_g, xo, xg, fo, fg
+
+
+@pytest.mark.parametrize("n,cin,cout,ks,stride", [
+    (5000, 4, 16, 3, 1), (5000, 16, 16, 3, 1), (6000, 32, 64, 3, 1), (3000, 96, 48, 3, 1), (2000, 128, 256, 3, 1),
+    (5000, 16, 16, 2, 2), (4000, 64, 64, 2, 2), (100, 16, 32, 3, 1), (1, 16, 16, 3, 1), (3000, 5, 7, 3, 1)])
+def test_conv3d_fwd_bwd(gpu, oracle, n, cin, cout, ks, stride):
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin * 3 + cout + ks)
+    conv_o, conv_g, xo, xg, fo, fg = _conv_case(oracle, gts, rng, n, cin, cout, ks, stride)
+    yo, yg = conv_o(xo), conv_g(xg)
+    assert torch.equal(yg.C.cpu(), yo.C) and yg.s == yo.s
+    assert rel_err(yg.F, yo.F) < FP32_REL
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    yg.F.backward(g.cuda())
+    assert rel_err(fg.grad, fo.grad) < FP32_REL
+    assert rel_err(conv_g.kernel.grad, conv_o.kernel.grad) < FP32_REL
+
+
+@pytest.mark.parametrize("cin,cmid,cout", [(16, 32, 16), (64, 96, 48)])
+def test_transposed_conv_fwd_bwd(gpu, oracle, cin, cmid, cout):
+    """down (k2 s2) then up (k2 s2 transposed) reusing the cached kernel map (build_blocks.py:43-47)."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(cin + cout)
+    down_o, down_g, xo, xg, fo, fg = _conv_case(oracle, gts, rng, 6000, cin, cmid, 2, 2)
+    up_o = oracle.Conv3d(cmid, cout, 2, 2, transposed=True)
+    up_g = gts.nn.Conv3d(cmid, cout, 2, 2, transposed=True)
+    up_g.load_state_dict(up_o.state_dict())
+    up_g.cuda()
+    xo.cmaps[xo.s] = xo.C
+    xg.cmaps[xg.s] = xg.C
+    yo, yg = up_o(down_o(xo)), up_g(down_g(xg))
+    assert yg.s == yo.s == (1, 1, 1)
+    assert torch.equal(yg.C.cpu(), yo.C)
+    assert rel_err(yg.F, yo.F) < FP32_REL
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    yg.F.backward(g.cuda())
+    assert rel_err(fg.grad, fo.grad) < FP32_REL
+    assert rel_err(up_g.kernel.grad, up_o.kernel.grad) < FP32_REL
+    assert rel_err(down_g.kernel.grad, down_o.kernel.grad) < FP32_REL
+
+
+# ---------------------------------------------------------------- whole model
+@pytest.mark.parametrize("cr,vs,seeds", [(0.5, 0.2, [0]), (0.5, 0.1, [1, 2])])
+def test_spvcnn_fwd_bwd_vs_oracle(gpu, oracle, cr, vs, seeds):
+    """SPVCNN (mirror of core/models/semantickitti/spvcnn.py) fwd + all parameter grads."""
+    from u2mkd_b200 import models, scans
+    import u2mkd_b200.torchsparse as gts
+    coords, feats = scans.make_batch(seeds, "nusc", 1, vs)
+    torch.manual_seed(0)
+    net_o = models.build_family(oracle.as_torchsparse_modules()["torchsparse"]).SPVCNN(cr=cr, pres=vs, vres=vs)
+    net_g = models.product().SPVCNN(cr=cr, pres=vs, vres=vs)
+    net_g.load_state_dict(net_o.state_dict())
+    net_g.cuda()
+    net_o.dropout = net_g.dropout = torch.nn.Identity()
+    target = torch.from_numpy(np.random.default_rng(0).integers(0, 17, size=coords.shape[0]))
+
+    def step(net, st_cls, dev):
+        x = st_cls(torch.from_numpy(feats).to(dev), torch.from_numpy(coords).to(dev))
+        out = net({"lidar": x})["x_vox"]
+        torch.nn.functional.cross_entropy(out, target.to(dev)).backward()
+        return out
+
+    out_g = step(net_g, gts.SparseTensor, "cuda")
+    out_o = step(net_o, oracle.SparseTensor, "cpu")
+    # 49 conv + BN layers deep: BN re-normalises, so errors do not grow, but summation order differs
+    assert rel_err(out_g, out_o) < 1e-3
+    # a Linear/conv bias directly in front of a BatchNorm has an exactly-zero true gradient: what is
+    # left there is rounding noise on both sides, so parameters whose oracle gradient is < 1e-6 of
+    # the largest gradient in the model are compared absolutely instead of relatively
+    gmax = max(float(p.grad.abs().max()) for p in net_o.parameters())
+    worst = 0.0
+    for (name, pg), (_, po) in zip(net_g.named_parameters(), net_o.named_parameters()):
+        if float(po.grad.abs().max()) < 1e-6 * gmax:
+            assert float((pg.grad.cpu() - po.grad).abs().max()) < 1e-6 * gmax, name
+        else:
+            worst = max(worst, rel_err(pg.grad, po.grad))
+    assert worst < 5e-3, worst
+
+
+def test_cpu_tensor_is_rejected(gpu):
+    c = torch.zeros((4, 4), dtype=torch.int)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gpu.sphash(c)

@@ -1,0 +1,76 @@
+// C-ABI dispatch of the sparse-convolution entry points (include/u2mkd.h).
+#include "u2_common.cuh"
+
+int u2_conv_fwd_simt(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
+                     int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, cudaStream_t st);
+int u2_conv_wgrad_simt(const float *X, int64_t n_src, int32_t Cs, const float *dY, int64_t n_dst, int32_t Cd,
+                       const int32_t *table, int64_t ld, int32_t K, float *dW, cudaStream_t st);
+
+#ifdef U2_WITH_TC
+size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math);
+int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t math);
+int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
+                   int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
+                   size_t scratch_bytes, cudaStream_t st);
+int u2_conv_wgrad_tc(const float *X, int64_t n_src, int32_t Cs, const float *dY, int64_t n_dst, int32_t Cd,
+                     const int32_t *table, int64_t ld, int32_t K, float *dW, int32_t math, void *scratch,
+                     size_t scratch_bytes, cudaStream_t st);
+#endif
+
+extern "C" int u2_has_tensor_core_path(void) {
+#ifdef U2_WITH_TC
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+extern "C" size_t u2_conv_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math) {
+#ifdef U2_WITH_TC
+    if (math != U2_MATH_FP32) return u2_conv_tc_scratch_bytes(n_dst, K, Cs, Cd, math);
+#endif
+    (void)n_dst; (void)K; (void)Cs; (void)Cd; (void)math;
+    return 0;
+}
+
+static int check_common(const void *X, const void *W, const void *table, const void *Y, int32_t Cs, int32_t Cd, int32_t K,
+                        int64_t ld, int64_t n_dst, const char *who) {
+    U2_CHECK_ARG(X && W && table && Y, "%s: null pointer", who);
+    U2_CHECK_ARG(Cs > 0 && Cd > 0 && K > 0, "%s: bad shape Cs=%d Cd=%d K=%d", who, Cs, Cd, K);
+    U2_CHECK_ARG(ld >= n_dst, "%s: ld < n_dst", who);
+    return 0;
+}
+
+extern "C" int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
+                           const int32_t *table, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
+                           void *scratch, size_t scratch_bytes, u2_stream_t stream) {
+    if (check_common(X, W, table, Y, Cs, Cd, K, ld, n_dst, "u2_conv_fwd")) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (math == U2_MATH_FP32) return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
+#ifdef U2_WITH_TC
+    if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, math))
+        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, st);
+    if (math == U2_MATH_TF32 || math == U2_MATH_BF16)  // shapes the MMA tiles cannot hold (e.g. Cs = 4 stem)
+        return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
+#endif
+    (void)scratch; (void)scratch_bytes;
+    u2_set_error("u2_conv_fwd: math mode %d not available in this build", math);
+    return 1;
+}
+
+extern "C" int u2_conv_wgrad(const float *X, int64_t n_src, int32_t Cs, const float *dY, int64_t n_dst, int32_t Cd,
+                             const int32_t *table, int64_t ld, int32_t K, float *dW, int32_t math, void *scratch,
+                             size_t scratch_bytes, u2_stream_t stream) {
+    if (check_common(X, dY, table, dW, Cs, Cd, K, ld, n_dst, "u2_conv_wgrad")) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (math == U2_MATH_FP32) return u2_conv_wgrad_simt(X, n_src, Cs, dY, n_dst, Cd, table, ld, K, dW, st);
+#ifdef U2_WITH_TC
+    if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, math))
+        return u2_conv_wgrad_tc(X, n_src, Cs, dY, n_dst, Cd, table, ld, K, dW, math, scratch, scratch_bytes, st);
+    if (math == U2_MATH_TF32 || math == U2_MATH_BF16)
+        return u2_conv_wgrad_simt(X, n_src, Cs, dY, n_dst, Cd, table, ld, K, dW, st);
+#endif
+    (void)scratch; (void)scratch_bytes;
+    u2_set_error("u2_conv_wgrad: math mode %d not available in this build", math);
+    return 1;
+}

@@ -1,0 +1,166 @@
+// Strided-conv output coordinates and kernel-map construction.
+// Replaces F.spdownsample and the sphash -> sphashquery -> nonzero sequence inside
+// torchsparse F.conv3d (see include/u2mkd.h). Integer, HBM/L2-bound: 16-byte coordinate
+// loads, 16-byte table slots, neighbour tables written as K coalesced int32 streams.
+#include <cub/cub.cuh>
+
+#include "u2_common.cuh"
+
+// ------------------------------------------------------------------ downsample
+#define U2_COORD_BITS 18
+#define U2_COORD_MAX (1 << U2_COORD_BITS)
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+__global__ void __launch_bounds__(256) downsample_key_kernel(const int4 *__restrict__ coords, int64_t n, int sx, int sy,
+                                                             int sz, unsigned long long *__restrict__ keys,
+                                                             int *__restrict__ err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 c = __ldg(coords + i);
+    int x = floor_div(c.x, sx) * sx, y = floor_div(c.y, sy) * sy, z = floor_div(c.z, sz) * sz;
+    if ((unsigned)x >= U2_COORD_MAX || (unsigned)y >= U2_COORD_MAX || (unsigned)z >= U2_COORD_MAX || (unsigned)c.w >= 1024u)
+        atomicExch(err, 1);
+    keys[i] = ((unsigned long long)(unsigned)c.w << (3 * U2_COORD_BITS)) | ((unsigned long long)(unsigned)x << (2 * U2_COORD_BITS)) |
+              ((unsigned long long)(unsigned)y << U2_COORD_BITS) | (unsigned long long)(unsigned)z;
+}
+
+__global__ void __launch_bounds__(256) downsample_unpack_kernel(const unsigned long long *__restrict__ keys,
+                                                                const int64_t *__restrict__ n_out, int4 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_out) return;
+    unsigned long long k = keys[i];
+    const unsigned m = U2_COORD_MAX - 1;
+    out[i] = make_int4((int)((k >> (2 * U2_COORD_BITS)) & m), (int)((k >> U2_COORD_BITS) & m), (int)(k & m),
+                       (int)(k >> (3 * U2_COORD_BITS)));
+}
+
+__global__ void downsample_poison_kernel(const int *err, int64_t *n_out) {
+    if (*err) *n_out = -1;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t downsample_cub_bytes(int64_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, a, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, n, 0, 64);
+    cub::DeviceSelect::Unique(nullptr, b, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                              (int64_t *)nullptr, n);
+    return align_up(a > b ? a : b);
+}
+
+extern "C" size_t u2_downsample_scratch_bytes(int64_t n) {
+    if (n <= 0) n = 1;
+    return 2 * align_up((size_t)n * 8) + 256 + downsample_cub_bytes(n);
+}
+
+extern "C" int u2_downsample_coords(const int32_t *coords, int64_t n, int32_t sx, int32_t sy, int32_t sz,
+                                    int32_t *out_coords, int64_t *n_out_dev, void *scratch, size_t scratch_bytes,
+                                    u2_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    U2_CHECK_ARG(sx > 0 && sy > 0 && sz > 0, "u2_downsample_coords: bad stride");
+    U2_CHECK_ARG(scratch_bytes >= u2_downsample_scratch_bytes(n), "u2_downsample_coords: scratch too small");
+    U2_CHECK_ARG((((uintptr_t)coords | (uintptr_t)out_coords | (uintptr_t)scratch) & 15) == 0,
+                 "u2_downsample_coords: pointers must be 16-byte aligned");
+    if (n == 0) {
+        U2_CUDA_OK(cudaMemsetAsync(n_out_dev, 0, 8, st));
+        return 0;
+    }
+    char *p = (char *)scratch;
+    unsigned long long *keys_a = (unsigned long long *)p; p += align_up((size_t)n * 8);
+    unsigned long long *keys_b = (unsigned long long *)p; p += align_up((size_t)n * 8);
+    int *err = (int *)p; p += 256;
+    size_t cub_bytes = downsample_cub_bytes(n);
+    U2_CUDA_OK(cudaMemsetAsync(err, 0, 4, st));
+    const unsigned grid = (unsigned)u2_ceil_div(n, 256);
+    downsample_key_kernel<<<grid, 256, 0, st>>>((const int4 *)coords, n, sx, sy, sz, keys_a, err);
+    U2_LAUNCH_OK();
+    U2_CUDA_OK(cub::DeviceRadixSort::SortKeys(p, cub_bytes, keys_a, keys_b, n, 0, 64, st));
+    U2_CUDA_OK(cub::DeviceSelect::Unique(p, cub_bytes, keys_b, keys_a, n_out_dev, n, st));
+    downsample_unpack_kernel<<<grid, 256, 0, st>>>(keys_a, n_out_dev, (int4 *)out_coords);
+    U2_LAUNCH_OK();
+    // range violations poison the count so the caller cannot miss them
+    downsample_poison_kernel<<<1, 1, 0, st>>>(err, n_out_dev);
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ kernel map
+__global__ void __launch_bounds__(256) coord_insert_kernel(const int4 *__restrict__ coords, int64_t n, U2Slot *table,
+                                                           unsigned long long mask) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 c = __ldg(coords + i);
+    u2_table_insert(table, mask, (unsigned long long)u2_fnv4(c.x, c.y, c.z, c.w), (unsigned int)i);
+}
+
+// grid.x over output rows (padded to ld_out), grid.y over slices of the K offsets.
+__global__ void __launch_bounds__(256) kmap_query_kernel(const U2Slot *__restrict__ table, unsigned long long mask,
+                                                         const int4 *__restrict__ out_coords, int64_t n_out, int64_t ld_out,
+                                                         const int *__restrict__ offsets, int K, int k_per_slice,
+                                                         int *__restrict__ nbr, int *__restrict__ nbrT, int64_t ld_in,
+                                                         int *__restrict__ nbsizes) {
+    extern __shared__ int smem[];
+    int *s_off = smem;           // [3*K]
+    int *s_cnt = smem + 3 * K;   // [K]
+    for (int t = threadIdx.x; t < 3 * K; t += blockDim.x) s_off[t] = offsets[t];
+    for (int t = threadIdx.x; t < K; t += blockDim.x) s_cnt[t] = 0;
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = row < n_out;
+    const int k0 = blockIdx.y * k_per_slice;
+    const int k1 = min(K, k0 + k_per_slice);
+    int4 c = make_int4(0, 0, 0, 0);
+    if (live) c = __ldg(out_coords + row);
+    for (int k = k0; k < k1; k++) {
+        int hit = -1;
+        if (live)
+            hit = u2_table_lookup(table, mask,
+                                  (unsigned long long)u2_fnv4(c.x + s_off[3 * k], c.y + s_off[3 * k + 1], c.z + s_off[3 * k + 2], c.w));
+        if (row < ld_out) nbr[(int64_t)k * ld_out + row] = hit;
+        if (hit >= 0) nbrT[(int64_t)k * ld_in + hit] = (int)row;
+        const unsigned b = __ballot_sync(0xffffffffu, hit >= 0);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(s_cnt + k, __popc(b));
+    }
+    __syncthreads();
+    for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x)
+        if (s_cnt[k]) atomicAdd(nbsizes + k, s_cnt[k]);
+}
+
+extern "C" size_t u2_kmap_scratch_bytes(int64_t n_in) { return u2_hash_table_bytes(n_in); }
+
+extern "C" int u2_kmap_build(const int32_t *in_coords, int64_t n_in, const int32_t *out_coords, int64_t n_out,
+                             const int32_t *offsets, int32_t K, int32_t *nbr, int64_t ld_out, int32_t *nbrT, int64_t ld_in,
+                             int32_t *nbsizes, void *scratch, size_t scratch_bytes, u2_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    U2_CHECK_ARG(K > 0 && K <= 1024, "u2_kmap_build: bad K=%d", K);
+    U2_CHECK_ARG(ld_out >= n_out && ld_in >= n_in, "u2_kmap_build: leading dimensions too small");
+    U2_CHECK_ARG(scratch_bytes >= u2_kmap_scratch_bytes(n_in), "u2_kmap_build: scratch too small");
+    U2_CHECK_ARG((((uintptr_t)in_coords | (uintptr_t)out_coords | (uintptr_t)scratch) & 15) == 0,
+                 "u2_kmap_build: pointers must be 16-byte aligned");
+    U2_CHECK_ARG(n_in < 0x7FFFFFFFLL && n_out < 0x7FFFFFFFLL, "u2_kmap_build: too many rows");
+    U2_CUDA_OK(cudaMemsetAsync(nbsizes, 0, K * sizeof(int), st));
+    if (ld_in > 0) U2_CUDA_OK(cudaMemsetAsync(nbrT, 0xFF, (size_t)K * ld_in * sizeof(int), st));
+    if (ld_out == 0) return 0;
+    const size_t tbytes = u2_hash_table_bytes(n_in);
+    U2_CUDA_OK(cudaMemsetAsync(scratch, 0xFF, tbytes, st));
+    const unsigned long long mask = tbytes / sizeof(U2Slot) - 1;
+    if (n_in > 0) {
+        coord_insert_kernel<<<(unsigned)u2_ceil_div(n_in, 256), 256, 0, st>>>((const int4 *)in_coords, n_in,
+                                                                            (U2Slot *)scratch, mask);
+        U2_LAUNCH_OK();
+    }
+    const int64_t row_blocks = u2_ceil_div(ld_out, 256);
+    int slices = 1;
+    while (slices < K && row_blocks * slices < (int64_t)U2_NUM_SMS * 16) slices++;
+    const int k_per_slice = (K + slices - 1) / slices;
+    slices = (K + k_per_slice - 1) / k_per_slice;
+    dim3 grid((unsigned)row_blocks, (unsigned)slices);
+    kmap_query_kernel<<<grid, 256, 4 * K * sizeof(int), st>>>((const U2Slot *)scratch, mask, (const int4 *)out_coords, n_out,
+                                                              ld_out, offsets, K, k_per_slice, nbr, nbrT, ld_in, nbsizes);
+    U2_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,325 @@
+"""Tensor-level bindings of the C-ABI (include/u2mkd.h): torch CUDA tensors in, raw device
+pointers + the current stream down, autograd Functions on top.
+
+This is the whole "torch extension": torch supplies device memory, streams and autograd
+plumbing; all arithmetic of the path runs in libu2mkd_b200.so.  CUDA tensors only — a CPU
+tensor raises (there is deliberately no CPU path in the product; the CPU restatement lives
+in oracle/ and is test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
+
+_MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
+_state = {"math": MATH_FP32}
+
+
+def set_math(mode: str) -> None:
+    """Arithmetic of the conv GEMMs: 'fp32' (FFMA, parity mode), 'tf32' or 'bf16' (tcgen05)."""
+    m = _MATH_NAMES[mode]
+    if m != MATH_FP32 and not lib().u2_has_tensor_core_path():
+        raise RuntimeError("this build of libu2mkd_b200.so has no tcgen05 conv path")
+    _state["math"] = m
+
+
+def get_math() -> str:
+    return {v: k for k, v in _MATH_NAMES.items()}[_state["math"]]
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("u2mkd_b200 ops need CUDA tensors (no CPU fallback); got a tensor on " + str(t.device))
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# -------------------------------------------------------------------------------- hashing
+def sphash(coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """spf.sphash (core/models/utils.py:19,43,49,86,92): int32 [N,4] (+[K,3]) -> int64 [N] / [K,N]."""
+    _need_cuda(coords, offsets)
+    assert coords.dtype == torch.int, coords.dtype
+    assert coords.ndim == 2 and coords.shape[1] == 4, coords.shape
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    if offsets is None:
+        out = torch.empty(n, dtype=torch.int64, device=coords.device)
+        check(lib().u2_hash(coords.data_ptr(), n, None, 0, out.data_ptr(), _st()))
+        return out
+    assert offsets.dtype == torch.int, offsets.dtype
+    assert offsets.ndim == 2 and offsets.shape[1] == 3, offsets.shape
+    offsets = offsets.contiguous()
+    K = offsets.shape[0]
+    out = torch.empty((K, n), dtype=torch.int64, device=coords.device)
+    check(lib().u2_hash(coords.data_ptr(), n, offsets.data_ptr(), K, out.data_ptr(), _st()))
+    return out
+
+
+def sphashquery(queries: torch.Tensor, references: torch.Tensor) -> torch.Tensor:
+    """spf.sphashquery (core/models/utils.py:21,50,93,135): position of each query in references, -1 if absent."""
+    _need_cuda(queries, references)
+    assert queries.dtype == torch.long and references.dtype == torch.long
+    sizes = queries.size()
+    q = queries.contiguous().view(-1)
+    references = references.contiguous()
+    n = references.shape[0]
+    tbytes = lib().u2_hash_table_bytes(n)
+    table = torch.empty(tbytes, dtype=torch.uint8, device=q.device)
+    st = _st()
+    check(lib().u2_hash_table_build(references.data_ptr(), n, table.data_ptr(), tbytes, st))
+    out = torch.empty(q.shape[0], dtype=torch.int64, device=q.device)
+    check(lib().u2_hash_table_query(table.data_ptr(), tbytes, q.data_ptr(), q.shape[0], out.data_ptr(), st))
+    return out.view(*sizes)
+
+
+def spcount(coords: torch.Tensor, num: int) -> torch.Tensor:
+    """spf.spcount (core/models/utils.py:22,51)."""
+    _need_cuda(coords)
+    assert coords.dtype == torch.int
+    coords = coords.contiguous()
+    out = torch.empty(int(num), dtype=torch.int, device=coords.device)
+    check(lib().u2_count(coords.data_ptr(), coords.shape[0], out.data_ptr(), int(num), _st()))
+    return out
+
+
+# -------------------------------------------------------------------------------- voxelize
+class VoxelizeFn(Function):
+    """spf.spvoxelize (core/models/utils.py:24,26,58): scatter-mean with autograd."""
+
+    @staticmethod
+    def forward(ctx, feats, coords, counts):
+        _need_cuda(feats, coords, counts)
+        in_dtype = feats.dtype
+        feats = feats.contiguous().float()
+        coords = coords.contiguous().int()
+        counts = counts.contiguous().int()
+        n_pts, c = feats.shape
+        n_vox = counts.shape[0]
+        out = torch.empty((n_vox, c), dtype=torch.float32, device=feats.device)
+        check(lib().u2_voxelize_fwd(feats.data_ptr(), n_pts, c, coords.data_ptr(), counts.data_ptr(), out.data_ptr(),
+                                    n_vox, _st()))
+        ctx.for_backwards = (coords, counts, n_pts, in_dtype)
+        return out.to(in_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        coords, counts, n_pts, in_dtype = ctx.for_backwards
+        g = grad_output.contiguous().float()
+        n_vox, c = g.shape
+        gin = torch.empty((n_pts, c), dtype=torch.float32, device=g.device)
+        check(lib().u2_voxelize_bwd(g.data_ptr(), n_vox, c, coords.data_ptr(), counts.data_ptr(), gin.data_ptr(), n_pts,
+                                    _st()))
+        return gin.to(in_dtype), None, None
+
+
+def spvoxelize(feats, coords, counts):
+    return VoxelizeFn.apply(feats, coords, counts)
+
+
+# -------------------------------------------------------------------------------- devoxelize
+def calc_ti_weights(coords: torch.Tensor, idx_query: torch.Tensor, scale: float = 1) -> torch.Tensor:
+    """spf.calc_ti_weights (core/models/utils.py:94): fp32 [N,4], int64 [8,N] -> fp32 [8,N]."""
+    _need_cuda(coords, idx_query)
+    with torch.no_grad():
+        coords = coords.contiguous().float()
+        assert coords.ndim == 2 and coords.shape[1] == 4, coords.shape
+        idx_query = idx_query.contiguous().long()
+        n = coords.shape[0]
+        assert idx_query.shape == (8, n), idx_query.shape
+        w = torch.empty((8, n), dtype=torch.float32, device=coords.device)
+        check(lib().u2_ti_weights(coords.data_ptr(), idx_query.data_ptr(), n, float(scale), w.data_ptr(), _st()))
+    return w
+
+
+class DevoxelizeFn(Function):
+    """spf.spdevoxelize (core/models/utils.py:99,111)."""
+
+    @staticmethod
+    def forward(ctx, feats, coords, weights):
+        _need_cuda(feats, coords, weights)
+        in_dtype = feats.dtype
+        feats = feats.contiguous().float()
+        coords = coords.contiguous().int()
+        weights = weights.contiguous().float()
+        n_vox, c = feats.shape
+        n_pts = coords.shape[0]
+        assert coords.shape == (n_pts, 8) and weights.shape == (n_pts, 8)
+        out = torch.empty((n_pts, c), dtype=torch.float32, device=feats.device)
+        check(lib().u2_devoxelize_fwd(feats.data_ptr(), n_vox, c, coords.data_ptr(), weights.data_ptr(), n_pts,
+                                      out.data_ptr(), _st()))
+        ctx.for_backwards = (coords, weights, n_vox, in_dtype)
+        return out.to(in_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        coords, weights, n_vox, in_dtype = ctx.for_backwards
+        g = grad_output.contiguous().float()
+        n_pts, c = g.shape
+        gf = torch.empty((n_vox, c), dtype=torch.float32, device=g.device)
+        check(lib().u2_devoxelize_bwd(g.data_ptr(), n_pts, c, coords.data_ptr(), weights.data_ptr(), gf.data_ptr(), n_vox,
+                                      _st()))
+        return gf.to(in_dtype), None, None
+
+
+def spdevoxelize(feats, coords, weights):
+    return DevoxelizeFn.apply(feats, coords, weights)
+
+
+# -------------------------------------------------------------------------------- kernel maps
+def downsample_coords(coords: torch.Tensor, sample_stride: Tuple[int, int, int]) -> torch.Tensor:
+    """Unique rows of (floor(c / s) * s, b), sorted by (b, x, y, z); one host sync for the row count."""
+    _need_cuda(coords)
+    assert coords.dtype == torch.int and coords.ndim == 2 and coords.shape[1] == 4
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    sbytes = lib().u2_downsample_scratch_bytes(n)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=coords.device)
+    out = torch.empty((n, 4), dtype=torch.int, device=coords.device)
+    n_out = torch.empty(1, dtype=torch.int64, device=coords.device)
+    check(lib().u2_downsample_coords(coords.data_ptr(), n, int(sample_stride[0]), int(sample_stride[1]),
+                                     int(sample_stride[2]), out.data_ptr(), n_out.data_ptr(), scratch.data_ptr(), sbytes,
+                                     _st()))
+    m = int(n_out.item())
+    if m < 0:
+        raise RuntimeError("downsample_coords: coordinates outside [0, 2^18) or batch outside [0, 1024)")
+    return out[:m]
+
+
+class KernelMap:
+    """Kernel map of one sparse Conv3d: dense neighbour tables on the device.
+
+    nbr  int32 [K, ld_out]: nbr[k, o]  = input row matching output row o at offset k, or -1
+    nbrT int32 [K, ld_in ]: nbrT[k, i] = output row of that pair, or -1
+    Indexing as a 3-list reproduces the reference contract read at
+    core/models/sphereformer/unet_spherical_transformer.py:226-232:
+    [nbmaps int64 [M,2] rows (in, out) ordered by (k, out), nbsizes [K], (N_in, N_out)].
+    """
+
+    def __init__(self, nbr, nbrT, nbsizes, n_in, n_out):
+        self.nbr, self.nbrT, self.nbsizes = nbr, nbrT, nbsizes
+        self.n_in, self.n_out = n_in, n_out
+        self.K = nbr.shape[0]
+        self._nbmaps = None
+
+    @property
+    def nbmaps(self) -> torch.Tensor:
+        if self._nbmaps is None:
+            res = self.nbr[:, :self.n_out]
+            nz = torch.nonzero(res != -1)
+            nz[:, 0] = res[nz[:, 0], nz[:, 1]].long()
+            self._nbmaps = nz
+        return self._nbmaps
+
+    @property
+    def sizes(self):
+        return (self.n_in, self.n_out)
+
+    def __getitem__(self, i):
+        return (self.nbmaps, self.nbsizes, self.sizes)[i]
+
+    def __len__(self):
+        return 3
+
+    def __iter__(self):
+        return iter((self.nbmaps, self.nbsizes, self.sizes))
+
+
+_PAD = 128
+
+
+def _pad(n: int) -> int:
+    return max(_PAD, (n + _PAD - 1) // _PAD * _PAD)
+
+
+def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets: torch.Tensor) -> KernelMap:
+    """For every output voxel o and offset k: the input voxel at coord(o) + offset_k."""
+    _need_cuda(in_coords, out_coords, offsets)
+    in_coords = in_coords.contiguous()
+    out_coords = out_coords.contiguous()
+    offsets = offsets.contiguous().int()
+    dev = in_coords.device
+    n_in, n_out, K = in_coords.shape[0], out_coords.shape[0], offsets.shape[0]
+    ld_in, ld_out = _pad(n_in), _pad(n_out)
+    nbr = torch.empty((K, ld_out), dtype=torch.int, device=dev)
+    nbrT = torch.empty((K, ld_in), dtype=torch.int, device=dev)
+    nbsizes = torch.empty(K, dtype=torch.int, device=dev)
+    sbytes = lib().u2_kmap_scratch_bytes(n_in)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    check(lib().u2_kmap_build(in_coords.data_ptr(), n_in, out_coords.data_ptr(), n_out, offsets.data_ptr(), K,
+                              nbr.data_ptr(), ld_out, nbrT.data_ptr(), ld_in, nbsizes.data_ptr(), scratch.data_ptr(),
+                              sbytes, _st()))
+    return KernelMap(nbr, nbrT, nbsizes, n_in, n_out)
+
+
+# -------------------------------------------------------------------------------- convolution
+def _conv_gather_gemm(x, w, w_transposed, table, n_dst, c_dst, math):
+    K, ld = table.shape
+    n_src, c_src = x.shape
+    y = torch.empty((n_dst, c_dst), dtype=torch.float32, device=x.device)
+    sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device) if sbytes else None
+    check(lib().u2_conv_fwd(x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K,
+                            c_dst, y.data_ptr(), math, _ptr(scratch), sbytes, _st()))
+    return y
+
+
+class ConvolutionFn(Function):
+    """ConvolutionFunction of torchsparse F.conv3d, one fused kernel per
+    direction instead of K gather/mm/scatter rounds."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool, math: int):
+        _need_cuda(feats, weight)
+        in_dtype = feats.dtype
+        feats = feats.contiguous().float()
+        weight = weight.contiguous().float()
+        K, cin, cout = weight.shape
+        assert K == kmap.K and feats.shape[1] == cin
+        if not transposed:
+            table, n_dst = kmap.nbr, kmap.n_out
+            assert feats.shape[0] == kmap.n_in, (feats.shape, kmap.sizes)
+        else:
+            table, n_dst = kmap.nbrT, kmap.n_in
+            assert feats.shape[0] == kmap.n_out, (feats.shape, kmap.sizes)
+        out = _conv_gather_gemm(feats, weight, False, table, n_dst, cout, math)
+        ctx.save_for_backward(feats, weight)
+        ctx.misc = (kmap, transposed, math, in_dtype)
+        return out.to(in_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        feats, weight = ctx.saved_tensors
+        kmap, transposed, math, in_dtype = ctx.misc
+        g = grad_output.contiguous().float()
+        K, cin, cout = weight.shape
+        grad_feats = grad_weight = None
+        fwd_table = kmap.nbrT if transposed else kmap.nbr
+        if ctx.needs_input_grad[0]:
+            bwd_table = kmap.nbr if transposed else kmap.nbrT
+            grad_feats = _conv_gather_gemm(g, weight, True, bwd_table, feats.shape[0], cin, math).to(in_dtype)
+        if ctx.needs_input_grad[1]:
+            grad_weight = torch.empty_like(weight)
+            n_dst = g.shape[0]
+            sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, math)
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device) if sbytes else None
+            check(lib().u2_conv_wgrad(feats.data_ptr(), feats.shape[0], cin, g.data_ptr(), n_dst, cout,
+                                      fwd_table.data_ptr(), fwd_table.shape[1], K, grad_weight.data_ptr(), math,
+                                      _ptr(scratch), sbytes, _st()))
+        return grad_feats, grad_weight, None, None, None
+
+
+def sparse_conv(feats, weight, kmap: KernelMap, transposed: bool = False, math: Optional[int] = None):
+    return ConvolutionFn.apply(feats, weight, kmap, transposed, _state["math"] if math is None else math)

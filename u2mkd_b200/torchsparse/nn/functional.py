@@ -1,0 +1,71 @@
+"""torchsparse.nn.functional: sphash / sphashquery / spcount / spvoxelize / spdevoxelize /
+calc_ti_weights / spdownsample / conv3d, all backed by libu2mkd_b200.so (include/u2mkd.h).
+Call sites: core/models/utils.py:19-26,43-58,84-99,133-135; conv3d through spnn.Conv3d."""
+import functools
+
+import torch
+
+from ... import ops
+from ...ops import calc_ti_weights, spcount, spdevoxelize, sphash, sphashquery, spvoxelize
+from ..tensor import SparseTensor
+from ..utils import make_ntuple
+from .utils import get_kernel_offsets
+
+__all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "spdownsample",
+           "conv3d"]
+
+
+def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1) -> torch.Tensor:
+    """Output coordinates of a strided conv, sorted by (b,x,y,z)."""
+    stride, kernel_size, tensor_stride = (make_ntuple(v, ndim=3) for v in (stride, kernel_size, tensor_stride))
+    sample_stride = tuple(stride[a] * tensor_stride[a] for a in range(3))
+    if all(stride[a] in (1, kernel_size[a]) for a in range(3)):
+        return ops.downsample_coords(coords, sample_stride)
+    # general case (no U2MKD model uses it): expand by the kernel offsets, keep the
+    # candidates that sit on the output lattice, then the same sorted-unique kernel
+    offsets = get_kernel_offsets(kernel_size, tensor_stride, device=coords.device)
+    kv = offsets.size(0)
+    ss = torch.tensor(sample_stride, dtype=torch.int, device=coords.device).unsqueeze(0)
+    cmin = torch.min(coords[:, :3], dim=0, keepdim=True).values
+    xyz = (coords[:, :3].unsqueeze(1) + offsets.unsqueeze(0)).view(-1, 3)
+    b = coords[:, 3:].repeat(1, kv).view(-1, 1)
+    keep = torch.all((xyz % ss == 0) & (xyz >= cmin), dim=1)
+    cand = torch.cat([xyz, b], dim=1)[keep].contiguous()
+    return ops.downsample_coords(cand, (1, 1, 1))
+
+
+def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, stride=1, dilation=1,
+           transposed: bool = False) -> SparseTensor:
+    """F.conv3d of torchsparse v1.4.0: kernel-map lookup/build, then
+    one fused gather-GEMM kernel (ops.ConvolutionFn) instead of K gather/mm/scatter rounds."""
+    feats, coords = input.feats, input.coords
+    kernel_size, stride, dilation = (make_ntuple(v, ndim=3) for v in (kernel_size, stride, dilation))
+    unit = (1, 1, 1)
+    if kernel_size == unit and stride == unit and dilation == unit:
+        feats = feats.matmul(weight)
+        out_stride = input.stride
+    elif not transposed:
+        out_stride = tuple(input.stride[a] * stride[a] for a in range(3))
+        key = (input.stride, kernel_size, stride, dilation)
+        kmap = input.kmaps.get(key)
+        if kmap is None:
+            offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=feats.device)
+            if any(s > 1 for s in stride):
+                coords = spdownsample(coords, stride, kernel_size, input.stride)
+            kmap = ops.build_kernel_map(input.coords, coords, offsets)
+            input.kmaps[key] = kmap
+        elif any(s > 1 for s in stride):
+            coords = input.cmaps[out_stride]  # upstream skips this on a cache hit
+        feats = ops.sparse_conv(feats, weight, kmap, transposed=False)
+    else:
+        out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
+        kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
+        feats = ops.sparse_conv(feats, weight, kmap, transposed=True)
+        coords = input.cmaps[out_stride]
+    if bias is not None:
+        feats = feats + bias
+    output = SparseTensor(coords=coords, feats=feats, stride=out_stride)
+    output.cmaps = input.cmaps
+    output.cmaps.setdefault(output.stride, output.coords)
+    output.kmaps = input.kmaps
+    return output
