@@ -1,0 +1,108 @@
+"""tcgen05 (TF32) sparse-conv kernels against the CPU oracle and against the fp32 FFMA kernels.
+Tolerance: north_star's bf16/tf32 bar, rel 2e-2 = max|a-b| / max|b| per tensor; the tensor-core
+path is additionally required to stay within 5e-3 of the fp32 kernel on these sizes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TF32_REL = 2e-2
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def rand_coords(rng, n, extent=24, batch=2):
+    c = np.concatenate([rng.integers(0, extent, size=(n, 3)), rng.integers(0, batch, size=(n, 1))], 1).astype(np.int32)
+    c = np.unique(c, axis=0)
+    rng.shuffle(c)
+    return torch.from_numpy(np.ascontiguousarray(c))
+
+
+@pytest.fixture(scope="module")
+def tc(cuda_lib):
+    from u2mkd_b200 import ops
+    if not cuda_lib.u2_has_tensor_core_path():
+        pytest.fail("library built without the tcgen05 path")
+    yield ops
+    ops.set_math("fp32")
+
+
+@pytest.mark.parametrize("n,cin,cout,ks,stride", [
+    (6000, 32, 64, 3, 1), (3000, 96, 48, 3, 1), (2000, 128, 256, 3, 1), (4000, 64, 64, 2, 2), (2000, 16, 16, 3, 1),
+    (1500, 512, 512, 3, 1), (3000, 192, 384, 3, 1), (129, 64, 64, 3, 1), (5000, 48, 96, 2, 2), (700, 768, 512, 3, 1)])
+def test_conv3d_tf32_fwd_bwd(tc, oracle, n, cin, cout, ks, stride):
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin + cout)
+    c = rand_coords(rng, n)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32))
+    conv_o = oracle.Conv3d(cin, cout, ks, stride)
+    conv_g = gts.nn.Conv3d(cin, cout, ks, stride)
+    conv_g.load_state_dict(conv_o.state_dict())
+    conv_g.cuda()
+    fo = f.clone().requires_grad_(True)
+    yo = conv_o(oracle.SparseTensor(fo, c))
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    res = {}
+    for mode in ("fp32", "tf32"):
+        tc.set_math(mode)
+        conv_g.zero_grad()
+        fg = f.clone().cuda().requires_grad_(True)
+        yg = conv_g(gts.SparseTensor(fg, c.cuda()))
+        yg.F.backward(g.cuda())
+        res[mode] = (yg.F.detach(), fg.grad.detach(), conv_g.kernel.grad.detach().clone())
+    for got, want, what in zip(res["tf32"], (yo.F, fo.grad, conv_o.kernel.grad), ("out", "dgrad", "wgrad")):
+        assert rel_err(got, want) < TF32_REL, what
+    for got, want, what in zip(res["tf32"], res["fp32"], ("out", "dgrad", "wgrad")):
+        assert rel_err(got, want) < 5e-3, what
+
+
+def test_transposed_conv_tf32(tc, oracle):
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(11)
+    c = rand_coords(rng, 6000)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], 64)).astype(np.float32))
+    down_o, up_o = oracle.Conv3d(64, 96, 2, 2), oracle.Conv3d(96, 32, 2, 2, transposed=True)
+    down_g, up_g = gts.nn.Conv3d(64, 96, 2, 2), gts.nn.Conv3d(96, 32, 2, 2, transposed=True)
+    down_g.load_state_dict(down_o.state_dict())
+    up_g.load_state_dict(up_o.state_dict())
+    down_g.cuda(), up_g.cuda()
+    tc.set_math("tf32")
+    fo = f.clone().requires_grad_(True)
+    fg = f.clone().cuda().requires_grad_(True)
+    xo, xg = oracle.SparseTensor(fo, c), gts.SparseTensor(fg, c.cuda())
+    xo.cmaps[xo.s] = xo.C
+    xg.cmaps[xg.s] = xg.C
+    yo, yg = up_o(down_o(xo)), up_g(down_g(xg))
+    assert rel_err(yg.F, yo.F) < TF32_REL
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    yg.F.backward(g.cuda())
+    assert rel_err(fg.grad, fo.grad) < TF32_REL
+    assert rel_err(up_g.kernel.grad, up_o.kernel.grad) < TF32_REL
+    assert rel_err(down_g.kernel.grad, down_o.kernel.grad) < TF32_REL
+
+
+def test_spvcnn_tf32_vs_oracle(tc, oracle):
+    """Whole model in the fast mode: logits within the tf32 bar of the fp32 CPU oracle."""
+    from u2mkd_b200 import models, scans
+    import u2mkd_b200.torchsparse as gts
+    coords, feats = scans.make_batch([3], "nusc", 1, 0.1)
+    torch.manual_seed(0)
+    net_o = models.build_family(oracle.as_torchsparse_modules()["torchsparse"]).SPVCNN(cr=1.0, pres=0.1, vres=0.1)
+    net_g = models.product().SPVCNN(cr=1.0, pres=0.1, vres=0.1)
+    net_g.load_state_dict(net_o.state_dict())
+    net_g.cuda()
+    net_o.dropout = net_g.dropout = torch.nn.Identity()
+    tc.set_math("tf32")
+    out_g = net_g({"lidar": gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())})["x_vox"]
+    out_g.square().mean().backward()
+    out_o = net_o({"lidar": oracle.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords))})["x_vox"]
+    out_o.square().mean().backward()
+    assert rel_err(out_g, out_o) < TF32_REL
+    ga, go = net_g.stem[3].kernel.grad, net_o.stem[3].kernel.grad
+    assert rel_err(ga, go) < 0.15  # stem gradient after 48 tf32 layers back-to-back (per-op bar is 2e-2)

@@ -8,13 +8,10 @@ int u2_conv_wgrad_simt(const float *X, int64_t n_src, int32_t Cs, const float *d
 
 #ifdef U2_WITH_TC
 size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math);
-int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t math);
+int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
                    size_t scratch_bytes, cudaStream_t st);
-int u2_conv_wgrad_tc(const float *X, int64_t n_src, int32_t Cs, const float *dY, int64_t n_dst, int32_t Cd,
-                     const int32_t *table, int64_t ld, int32_t K, float *dW, int32_t math, void *scratch,
-                     size_t scratch_bytes, cudaStream_t st);
 #endif
 
 extern "C" int u2_has_tensor_core_path(void) {
@@ -48,9 +45,9 @@ extern "C" int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const floa
     cudaStream_t st = (cudaStream_t)stream;
     if (math == U2_MATH_FP32) return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #ifdef U2_WITH_TC
-    if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, math))
+    if (math == U2_MATH_TF32 && u2_conv_tc_supported(Cs, Cd, K, math))
         return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, st);
-    if (math == U2_MATH_TF32 || math == U2_MATH_BF16)  // shapes the MMA tiles cannot hold (e.g. Cs = 4 stem)
+    if (math == U2_MATH_TF32)  // shapes the MMA tiles cannot hold (e.g. the Cs = 4 stem conv)
         return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #endif
     (void)scratch; (void)scratch_bytes;
@@ -65,9 +62,7 @@ extern "C" int u2_conv_wgrad(const float *X, int64_t n_src, int32_t Cs, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (math == U2_MATH_FP32) return u2_conv_wgrad_simt(X, n_src, Cs, dY, n_dst, Cd, table, ld, K, dW, st);
 #ifdef U2_WITH_TC
-    if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, math))
-        return u2_conv_wgrad_tc(X, n_src, Cs, dY, n_dst, Cd, table, ld, K, dW, math, scratch, scratch_bytes, st);
-    if (math == U2_MATH_TF32 || math == U2_MATH_BF16)
+    if (math == U2_MATH_TF32)  // wgrad still runs the FFMA kernel (fp32-exact) in this build
         return u2_conv_wgrad_simt(X, n_src, Cs, dY, n_dst, Cd, table, ld, K, dW, st);
 #endif
     (void)scratch; (void)scratch_bytes;

@@ -1,0 +1,375 @@
+// Sparse convolution on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a only.
+// U2_MATH_TF32: fp32 storage, kind::tf32 MMA, fp32 accumulation in TMEM.
+//
+// fwd / dgrad  (u2_conv_fwd_tc): output-stationary implicit GEMM.
+//   CTA  = 128 destination rows x NT output channels (UMMA M=128, N=NT<=256, K=8/instr).
+//   item = (kernel offset k with >=1 valid neighbour in the tile) x (32-channel slice of Cs).
+//   warps 0-3 : A producers — gather the 128 neighbour rows of the slice with 16-byte
+//               cp.async (zero-fill for missing neighbours) straight into the canonical
+//               K-major no-swizzle UMMA layout; completion lands on the stage's mbarrier.
+//               Afterwards the same warps are the epilogue (TMEM -> registers -> HBM).
+//   warp 4    : B producer — one cp.async.bulk (TMA engine, UBLKCP) per item from the
+//               pre-tiled weight blob (already in UMMA layout), complete_tx on the mbarrier.
+//   warp 5    : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees the
+//               stage / publishes the accumulator.
+//   No gather buffer, no output read-modify-write, no atomics: every output row is written
+//   once; (tile, offset) pairs without neighbours are skipped.
+#include <cuda.h>
+
+#include "u2_common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+// ---------------------------------------------------------------- async copies
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor; version_=1 for Blackwell):
+//   K-major : core matrix = 8 rows x 16 B contiguous; SBO = stride between 8-row groups (M/N),
+//             LBO = stride between the two 16-byte K chunks of one MMA.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// Instruction descriptor (cute InstrDescriptor): F32 accumulate, TF32 x TF32, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int A_ROW_GROUP = TILE_M * 16;      // 2048: bytes of one 16-byte K chunk over 128 rows
+constexpr int A_LBO = A_ROW_GROUP + 16;       // +16: bank-conflict-free 16-byte gather writes
+
+struct FwdParams {
+    const float *X;
+    const float *Wt;  // pre-tiled weights
+    const int *table;
+    float *Y;
+    int64_t ld, n_dst;
+    int Cs, Cd, K, NT, stages, tmem_cols;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParams p) {
+    constexpr int CHUNKS = KC / 4;  // 16-byte chunks per row per stage
+    constexpr int A_BYTES = CHUNKS * A_LBO;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int NT = p.NT;
+    const int B_LBO = NT * 16;
+    const int B_BYTES = CHUNKS * B_LBO;
+    const int stage_bytes = A_BYTES + B_BYTES;
+    uint8_t *s_stage = smem;
+    int *s_tab = reinterpret_cast<int *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_tab + p.K * TILE_M);
+    uint64_t *s_empty = s_full + MAX_STAGES;
+    uint64_t *s_accum = s_empty + MAX_STAGES;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_accum + 1);
+    uint32_t *s_mask = s_tmem + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+    const int nt = blockIdx.y;
+    const int n_cc = p.Cs / KC;
+    const int n_nt = p.Cd / NT;
+
+    if (tid == 0) {
+        *s_mask = 0;
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(s_full + s, TILE_M + 1);
+            mbar_init(s_empty + s, 1);
+        }
+        mbar_init(s_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    __syncthreads();
+    // neighbour table of this tile -> smem, and the set of offsets that have any neighbour
+    for (int k = warp; k < p.K; k += NUM_THREADS / 32) {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < TILE_M / 32; j++) {
+            const int r = lane + 32 * j;
+            const int v = __ldg(p.table + (int64_t)k * p.ld + row0 + r);
+            s_tab[k * TILE_M + r] = v;
+            any |= v >= 0;
+        }
+        if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(s_mask, 1u << k);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t kmask = *s_mask;
+    const uint32_t tmem_base = *s_tmem;
+    const int n_items = __popc(kmask) * n_cc;
+
+    if (warp < 4) {
+        // ============================ A producers ============================
+        int it = 0;
+        for (uint32_t m = kmask; m; m &= m - 1) {
+            const int k = __ffs(m) - 1;
+            const int *tab_k = s_tab + k * TILE_M;
+            for (int cc = 0; cc < n_cc; cc++, it++) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(s_empty + s, ph ^ 1u);
+                const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
+                const float *xcol = p.X + cc * KC;
+#pragma unroll
+                for (int i = 0; i < CHUNKS; i++) {
+                    const int piece = i * TILE_M + tid;
+                    const int row = piece / CHUNKS, chunk = piece % CHUNKS;
+                    const int src = tab_k[row];
+                    const float *g = xcol + (int64_t)(src >= 0 ? src : 0) * p.Cs + chunk * 4;
+                    cp_async16(a_base + chunk * A_LBO + row * 16, g, src >= 0 ? 16u : 0u);
+                }
+                cp_async_mbar_arrive_noinc(s_full + s);
+            }
+        }
+        // ============================ epilogue ============================
+        const int64_t row = row0 + warp * 32 + lane;
+        float *yrow = p.Y + row * p.Cd + nt * NT;
+        if (n_items > 0) {
+            mbar_wait(s_accum, 0);
+            tc_fence_after();
+        }
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t v[16];
+            if (n_items > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = 0u;
+            }
+            if (row < p.n_dst) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    } else if (warp == 4) {
+        // ============================ B producer ============================
+        if (lane == 0) {
+            int it = 0;
+            for (uint32_t m = kmask; m; m &= m - 1) {
+                const int k = __ffs(m) - 1;
+                for (int cc = 0; cc < n_cc; cc++, it++) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(s_empty + s, ph ^ 1u);
+                    const uint32_t b_base = smem_u32(s_stage + (size_t)s * stage_bytes + A_BYTES);
+                    const float *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(KC * NT);
+                    mbar_arrive_expect_tx(s_full + s, (uint32_t)B_BYTES);
+                    bulk_g2s(b_base, blob, (uint32_t)B_BYTES, s_full + s);
+                }
+            }
+        }
+    } else {
+        // ============================ MMA issuer ============================
+        const uint32_t idesc = make_idesc_tf32(TILE_M, NT);
+        for (int it = 0; it < n_items; it++) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(s_full + s, ph);
+            tc_fence_after();
+            proxy_fence_async();
+            if (lane == 0) {
+                const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
+                const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < KC / 8; kk++) {
+                    const uint64_t ad = make_smem_desc(a_base + kk * 2 * A_LBO, A_LBO, 128);
+                    const uint64_t bd = make_smem_desc(b_base + kk * 2 * B_LBO, B_LBO, 128);
+                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(s_empty + s);
+                if (it == n_items - 1) umma_commit(s_accum);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// W [K][Cs][Cd] (or [K][Cd][Cs] if WT) -> blobs [k][cc][nt][chunk][n][4] in UMMA K-major layout
+template <bool WT>
+__global__ void __launch_bounds__(256) pretile_weights_kernel(const float *__restrict__ W, float4 *__restrict__ out, int K,
+                                                              int Cs, int Cd, int KC, int NT) {
+    const int64_t total = (int64_t)K * Cs * Cd / 4;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int chunks = KC / 4, n_cc = Cs / KC, n_nt = Cd / NT;
+    int64_t r = t;
+    const int n = (int)(r % NT); r /= NT;
+    const int chunk = (int)(r % chunks); r /= chunks;
+    const int nti = (int)(r % n_nt); r /= n_nt;
+    const int cc = (int)(r % n_cc); r /= n_cc;
+    const int k = (int)r;
+    const int cs = cc * KC + chunk * 4, cd = nti * NT + n;
+    float4 v;
+    if (WT) {
+        v = __ldg(reinterpret_cast<const float4 *>(W + ((int64_t)k * Cd + cd) * Cs + cs));
+    } else {
+        const float *src = W + ((int64_t)k * Cs + cs) * Cd + cd;
+        v = make_float4(__ldg(src), __ldg(src + Cd), __ldg(src + 2 * (int64_t)Cd), __ldg(src + 3 * (int64_t)Cd));
+    }
+    out[t] = v;
+}
+
+int pick_nt(int Cd) {
+    const int tiles = (Cd + 255) / 256;
+    if (Cd % tiles) return 0;
+    const int nt = Cd / tiles;
+    return (nt % 16 == 0 && nt >= 16) ? nt : 0;
+}
+
+int pick_kc(int Cs) { return Cs % 32 == 0 ? 32 : (Cs % 16 == 0 ? 16 : 0); }
+
+}  // namespace
+
+int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math) {
+    return math == U2_MATH_TF32 && pick_kc(Cs) && pick_nt(Cd) && K <= 32;
+}
+
+size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math) {
+    (void)n_dst;
+    if (!u2_conv_tc_supported(Cs, Cd, K, math)) return 0;
+    return (size_t)K * Cs * Cd * sizeof(float);
+}
+
+int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
+                   int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
+                   size_t scratch_bytes, cudaStream_t st) {
+    (void)n_src; (void)math;
+    if (n_dst == 0) return 0;
+    const int KC = pick_kc(Cs), NT = pick_nt(Cd);
+    U2_CHECK_ARG(KC && NT && K <= 32, "u2_conv_fwd_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
+    U2_CHECK_ARG(ld % TILE_M == 0, "u2_conv_fwd_tc: table leading dimension must be a multiple of 128");
+    U2_CHECK_ARG(scratch && scratch_bytes >= (size_t)K * Cs * Cd * sizeof(float), "u2_conv_fwd_tc: scratch too small");
+    U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)scratch) & 15) == 0,
+                 "u2_conv_fwd_tc: pointers must be 16-byte aligned");
+    const int64_t total4 = (int64_t)K * Cs * Cd / 4;
+    if (w_transposed)
+        pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
+    else
+        pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
+    U2_LAUNCH_OK();
+
+    FwdParams p;
+    p.X = X; p.Wt = (const float *)scratch; p.table = table; p.Y = Y;
+    p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
+    int cols = 32;
+    while (cols < NT) cols <<= 1;
+    p.tmem_cols = cols;
+    const int chunks = KC / 4;
+    const size_t stage_bytes = (size_t)chunks * A_LBO + (size_t)chunks * NT * 16;
+    const size_t fixed = (size_t)K * TILE_M * sizeof(int) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
+    // prefer two CTAs per SM (one gathers while the other drains its accumulator) if that
+    // still leaves >= 3 stages each; otherwise one CTA with as many stages as fit
+    const size_t budget = 227 * 1024;
+    int stages = (int)((budget / 2 - fixed - 1024) / stage_bytes);
+    if (stages < 3) stages = (int)((budget - fixed) / stage_bytes);
+    U2_CHECK_ARG(stages >= 2, "u2_conv_fwd_tc: tile does not fit shared memory");
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + fixed;
+    dim3 grid((unsigned)u2_ceil_div(n_dst, TILE_M), (unsigned)(Cd / NT));
+    if (KC == 32) {
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(p);
+    } else {
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_tc_kernel<16><<<grid, NUM_THREADS, smem, st>>>(p);
+    }
+    U2_LAUNCH_OK();
+    return 0;
+}

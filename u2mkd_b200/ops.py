@@ -20,6 +20,15 @@ from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
 _MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
 _state = {"math": MATH_FP32}
 
+# instrumentation used by bench.py: number of kernels this library launched, and an optional
+# per-launch CUDA-event timer for the conv kernels (the dominant kernel of the path)
+stats = {"launches": 0}
+conv_timer = None  # object with .record(kind, table, n_dst, K, c_src, c_dst, ev_start, ev_stop)
+
+
+def _count(n: int = 1) -> None:
+    stats["launches"] += n
+
 
 def set_math(mode: str) -> None:
     """Arithmetic of the conv GEMMs: 'fp32' (FFMA, parity mode), 'tf32' or 'bf16' (tcgen05)."""
@@ -58,6 +67,7 @@ def sphash(coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torc
     if offsets is None:
         out = torch.empty(n, dtype=torch.int64, device=coords.device)
         check(lib().u2_hash(coords.data_ptr(), n, None, 0, out.data_ptr(), _st()))
+        _count()
         return out
     assert offsets.dtype == torch.int, offsets.dtype
     assert offsets.ndim == 2 and offsets.shape[1] == 3, offsets.shape
@@ -65,6 +75,7 @@ def sphash(coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torc
     K = offsets.shape[0]
     out = torch.empty((K, n), dtype=torch.int64, device=coords.device)
     check(lib().u2_hash(coords.data_ptr(), n, offsets.data_ptr(), K, out.data_ptr(), _st()))
+    _count()
     return out
 
 
@@ -82,6 +93,7 @@ def sphashquery(queries: torch.Tensor, references: torch.Tensor) -> torch.Tensor
     check(lib().u2_hash_table_build(references.data_ptr(), n, table.data_ptr(), tbytes, st))
     out = torch.empty(q.shape[0], dtype=torch.int64, device=q.device)
     check(lib().u2_hash_table_query(table.data_ptr(), tbytes, q.data_ptr(), q.shape[0], out.data_ptr(), st))
+    _count(2)
     return out.view(*sizes)
 
 
@@ -92,6 +104,7 @@ def spcount(coords: torch.Tensor, num: int) -> torch.Tensor:
     coords = coords.contiguous()
     out = torch.empty(int(num), dtype=torch.int, device=coords.device)
     check(lib().u2_count(coords.data_ptr(), coords.shape[0], out.data_ptr(), int(num), _st()))
+    _count()
     return out
 
 
@@ -111,6 +124,7 @@ class VoxelizeFn(Function):
         out = torch.empty((n_vox, c), dtype=torch.float32, device=feats.device)
         check(lib().u2_voxelize_fwd(feats.data_ptr(), n_pts, c, coords.data_ptr(), counts.data_ptr(), out.data_ptr(),
                                     n_vox, _st()))
+        _count()
         ctx.for_backwards = (coords, counts, n_pts, in_dtype)
         return out.to(in_dtype)
 
@@ -122,6 +136,7 @@ class VoxelizeFn(Function):
         gin = torch.empty((n_pts, c), dtype=torch.float32, device=g.device)
         check(lib().u2_voxelize_bwd(g.data_ptr(), n_vox, c, coords.data_ptr(), counts.data_ptr(), gin.data_ptr(), n_pts,
                                     _st()))
+        _count()
         return gin.to(in_dtype), None, None
 
 
@@ -141,6 +156,7 @@ def calc_ti_weights(coords: torch.Tensor, idx_query: torch.Tensor, scale: float 
         assert idx_query.shape == (8, n), idx_query.shape
         w = torch.empty((8, n), dtype=torch.float32, device=coords.device)
         check(lib().u2_ti_weights(coords.data_ptr(), idx_query.data_ptr(), n, float(scale), w.data_ptr(), _st()))
+        _count()
     return w
 
 
@@ -160,6 +176,7 @@ class DevoxelizeFn(Function):
         out = torch.empty((n_pts, c), dtype=torch.float32, device=feats.device)
         check(lib().u2_devoxelize_fwd(feats.data_ptr(), n_vox, c, coords.data_ptr(), weights.data_ptr(), n_pts,
                                       out.data_ptr(), _st()))
+        _count()
         ctx.for_backwards = (coords, weights, n_vox, in_dtype)
         return out.to(in_dtype)
 
@@ -171,6 +188,7 @@ class DevoxelizeFn(Function):
         gf = torch.empty((n_vox, c), dtype=torch.float32, device=g.device)
         check(lib().u2_devoxelize_bwd(g.data_ptr(), n_pts, c, coords.data_ptr(), weights.data_ptr(), gf.data_ptr(), n_vox,
                                       _st()))
+        _count()
         return gf.to(in_dtype), None, None
 
 
@@ -192,6 +210,7 @@ def downsample_coords(coords: torch.Tensor, sample_stride: Tuple[int, int, int])
     check(lib().u2_downsample_coords(coords.data_ptr(), n, int(sample_stride[0]), int(sample_stride[1]),
                                      int(sample_stride[2]), out.data_ptr(), n_out.data_ptr(), scratch.data_ptr(), sbytes,
                                      _st()))
+    _count(4)
     m = int(n_out.item())
     if m < 0:
         raise RuntimeError("downsample_coords: coordinates outside [0, 2^18) or batch outside [0, 1024)")
@@ -261,18 +280,33 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets:
     check(lib().u2_kmap_build(in_coords.data_ptr(), n_in, out_coords.data_ptr(), n_out, offsets.data_ptr(), K,
                               nbr.data_ptr(), ld_out, nbrT.data_ptr(), ld_in, nbsizes.data_ptr(), scratch.data_ptr(),
                               sbytes, _st()))
+    _count(2)
     return KernelMap(nbr, nbrT, nbsizes, n_in, n_out)
 
 
 # -------------------------------------------------------------------------------- convolution
-def _conv_gather_gemm(x, w, w_transposed, table, n_dst, c_dst, math):
+def _timed(kind, kmap, n_dst, K, c_src, c_dst, launch):
+    """Run `launch()`; if bench.py installed a conv timer, bracket it with CUDA events on the
+    launching stream."""
+    _count()
+    if conv_timer is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    conv_timer.record(kind, kmap, n_dst, K, c_src, c_dst, e0, e1)
+
+
+def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math):
     K, ld = table.shape
     n_src, c_src = x.shape
     y = torch.empty((n_dst, c_dst), dtype=torch.float32, device=x.device)
     sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device) if sbytes else None
-    check(lib().u2_conv_fwd(x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K,
-                            c_dst, y.data_ptr(), math, _ptr(scratch), sbytes, _st()))
+    _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd(
+        x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
+        math, _ptr(scratch), sbytes, _st())))
     return y
 
 
@@ -294,7 +328,7 @@ class ConvolutionFn(Function):
         else:
             table, n_dst = kmap.nbrT, kmap.n_in
             assert feats.shape[0] == kmap.n_out, (feats.shape, kmap.sizes)
-        out = _conv_gather_gemm(feats, weight, False, table, n_dst, cout, math)
+        out = _conv_gather_gemm("fwd", kmap, feats, weight, False, table, n_dst, cout, math)
         ctx.save_for_backward(feats, weight)
         ctx.misc = (kmap, transposed, math, in_dtype)
         return out.to(in_dtype)
@@ -309,15 +343,16 @@ class ConvolutionFn(Function):
         fwd_table = kmap.nbrT if transposed else kmap.nbr
         if ctx.needs_input_grad[0]:
             bwd_table = kmap.nbr if transposed else kmap.nbrT
-            grad_feats = _conv_gather_gemm(g, weight, True, bwd_table, feats.shape[0], cin, math).to(in_dtype)
+            grad_feats = _conv_gather_gemm("dgrad", kmap, g, weight, True, bwd_table, feats.shape[0], cin,
+                                           math).to(in_dtype)
         if ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
             n_dst = g.shape[0]
             sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, math)
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device) if sbytes else None
-            check(lib().u2_conv_wgrad(feats.data_ptr(), feats.shape[0], cin, g.data_ptr(), n_dst, cout,
-                                      fwd_table.data_ptr(), fwd_table.shape[1], K, grad_weight.data_ptr(), math,
-                                      _ptr(scratch), sbytes, _st()))
+            _timed("wgrad", kmap, n_dst, K, cin, cout, lambda: check(lib().u2_conv_wgrad(
+                feats.data_ptr(), feats.shape[0], cin, g.data_ptr(), n_dst, cout, fwd_table.data_ptr(),
+                fwd_table.shape[1], K, grad_weight.data_ptr(), math, _ptr(scratch), sbytes, _st())))
         return grad_feats, grad_weight, None, None, None
 
 
