@@ -131,6 +131,24 @@ int u2_conv_wgrad(const float *X, int64_t n_src, int32_t Cs, const float *dY, in
                   int32_t Cd, const int32_t *table, int64_t ld, int32_t K, float *dW,
                   int32_t math, void *scratch, size_t scratch_bytes, u2_stream_t stream);
 
+/* ---- compacted pair list of a kernel map (the reference's (k, out)-ordered nbmaps
+ * [TS nn/functional/conv.py: nonzero(results != -1)], without the host sync):
+ * flat[j] = k*ld + out_row of the j-th valid entry of nbr [K, ld], ascending. `flat` needs room
+ * for every valid entry (<= total = K*ld). scratch from u2_kmap_pairs_scratch_bytes(total).      */
+size_t u2_kmap_pairs_scratch_bytes(int64_t total);
+int u2_kmap_pairs(const int32_t *nbr, int64_t total, int32_t *flat, void *scratch, size_t scratch_bytes,
+                  u2_stream_t stream);
+
+/* ---- wgrad over the compacted pair list (tcgen05 path; same result as u2_conv_wgrad):
+ * dW[k] (Cs x Cd) = sum over pairs (i, o) of offset k of  Xa[a,:]^T (outer) dYb[b,:],
+ * (a, b) = (i, o) for a regular conv (swap = 0: Xa = layer input, dYb = grad of the output) and
+ * (o, i) for a transposed conv (swap = 1). n_rows = number of rows on the `out` side of nbr.
+ * dW is zeroed by the call.                                                                        */
+int u2_conv_wgrad_pairs_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
+int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb, int32_t Cd, const int32_t *nbr, int64_t ld,
+                        int64_t n_rows, int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap,
+                        float *dW, int32_t math, u2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,8 @@ int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
                    size_t scratch_bytes, cudaStream_t st);
+int u2_conv_wgrad_tc(const float *X, int32_t Cs, const float *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
+                     int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, cudaStream_t st);
 #endif
 
 extern "C" int u2_has_tensor_core_path(void) {
@@ -68,4 +70,26 @@ extern "C" int u2_conv_wgrad(const float *X, int64_t n_src, int32_t Cs, const fl
     (void)scratch; (void)scratch_bytes;
     u2_set_error("u2_conv_wgrad: math mode %d not available in this build", math);
     return 1;
+}
+
+extern "C" int u2_conv_wgrad_pairs_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math) {
+#ifdef U2_WITH_TC
+    return math == U2_MATH_TF32 && u2_conv_tc_supported(32, Cd, K, math) && Cs % 4 == 0;
+#else
+    (void)Cs; (void)Cd; (void)K; (void)math;
+    return 0;
+#endif
+}
+
+extern "C" int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb, int32_t Cd, const int32_t *nbr, int64_t ld,
+                                   int64_t n_rows, int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap,
+                                   float *dW, int32_t math, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    U2_CHECK_ARG(Xa && dYb && nbr && flat && nbsizes && dW, "u2_conv_wgrad_pairs: null pointer");
+    U2_CHECK_ARG(u2_conv_wgrad_pairs_supported(Cs, Cd, K, math), "u2_conv_wgrad_pairs: unsupported shape/math");
+    return u2_conv_wgrad_tc(Xa, Cs, dYb, Cd, nbr, ld, n_rows, K, flat, nbsizes, swap, dW, (cudaStream_t)stream);
+#else
+    u2_set_error("u2_conv_wgrad_pairs: built without the tcgen05 path");
+    return 1;
+#endif
 }

@@ -15,6 +15,7 @@
 //   No gather buffer, no output read-modify-write, no atomics: every output row is written
 //   once; (tile, offset) pairs without neighbours are skipped.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "u2_common.cuh"
 
@@ -305,6 +306,186 @@ __global__ void __launch_bounds__(256) pretile_weights_kernel(const float *__res
     out[t] = v;
 }
 
+// ------------------------------------------------------------------ wgrad
+// dW[k] (Cs x Cd) = sum over the pairs of offset k of  Xrow^T (outer) dYrow.
+// MMA view: D[M = 128 input channels][N = NT output channels] += A[M x 8 pairs] * B[8 pairs x N].
+// Both operands are MN-major (a gathered row IS contiguous along M resp. N).  For 32-bit
+// operands the only MN-major shared-memory layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is
+// the only available smem layout"): atoms of 32 channels (128 B) x 4 pairs, Swizzle<2,5,2> on
+// the byte address = the 32-byte chunk index XORed with the pair index mod 4.  16-byte cp.async
+// pieces stay whole, only their destination moves:
+//   addr(pair r, 16-B chunk c) = (c / 8) * 4096 + r * 128 + ((((c % 8) >> 1) ^ (r & 3)) << 1 | (c & 1)) * 16
+//   (LBO = 4096 between channel atoms, SBO = 512 between groups of 4 pairs)
+// CTA = (offset k, chunk of WG_PAIRS pairs, 128-channel slice of Cs, NT-channel slice of Cd);
+// the pair list is the kernel map's compacted list (ascending k, then output row), so no MMA
+// cycle and no gathered byte is spent on missing neighbours.  Partial tiles are combined with
+// 16-byte fp32 reductions into dW (zeroed by the caller).
+constexpr int WG_PAIRS = 4096;  // pairs per CTA
+constexpr int WG_KR = 32;       // pairs per pipeline stage (4 MMAs of K=8)
+constexpr int WG_ATOM = WG_KR * 128;  // 4096 bytes: 32 pairs x 32 channels
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+    return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);  // SWIZZLE_128B_BASE32B
+}
+// physical 16-byte chunk of logical chunk c (0..7) in pair row r of a SW128_32B atom
+__device__ __forceinline__ int swz_chunk(int c, int r) { return ((((c >> 1) ^ (r & 3)) << 1) | (c & 1)); }
+
+struct WgradParams {
+    const float *X;    // rows indexed by the "a" side of a pair
+    const float *dY;   // rows indexed by the "b" side
+    const int *nbr;    // [K, ld] neighbour table the pair list was compacted from
+    const int *flat;   // compacted flat indices k*ld + out_row of the valid entries
+    const int *nbsizes;
+    float *dW;
+    int64_t ld;
+    int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int NT = p.NT;
+    const int n_batoms = (NT + 31) / 32;
+    constexpr int A_BYTES = 4 * WG_ATOM;  // 16 KB
+    const int B_BYTES = n_batoms * WG_ATOM;
+    const int stage_bytes = A_BYTES + B_BYTES;
+    int2 *s_pairs = reinterpret_cast<int2 *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_pairs + WG_PAIRS);
+    uint64_t *s_empty = s_full + MAX_STAGES;
+    uint64_t *s_accum = s_empty + MAX_STAGES;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_accum + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = blockIdx.y;
+    const int mt = blockIdx.z / p.n_nt, nt = blockIdx.z % p.n_nt;
+    // pair range of this CTA (all threads compute the same scalar prefix over <= 32 sizes)
+    int koff = 0;
+    for (int j = 0; j < k; j++) koff += __ldg(p.nbsizes + j);
+    const int n_k = __ldg(p.nbsizes + k);
+    const int c0 = blockIdx.x * WG_PAIRS;
+    if (c0 >= n_k) return;
+    const int n_pairs = min(WG_PAIRS, n_k - c0);
+    const int n_items = (n_pairs + WG_KR - 1) / WG_KR;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(s_full + s, TILE_M);
+            mbar_init(s_empty + s, 1);
+        }
+        mbar_init(s_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    // (a-row, b-row) of every pair of the chunk; padded to a whole stage with -1
+    {
+        const int *flat = p.flat + koff + c0;
+        const int padded = n_items * WG_KR;
+        for (int pr = tid; pr < padded; pr += NUM_THREADS) {
+            int2 ab = make_int2(-1, -1);
+            if (pr < n_pairs) {
+                const int f = __ldg(flat + pr);
+                const int o = f - k * (int)p.ld;
+                const int i = __ldg(p.nbr + f);
+                ab = p.swap ? make_int2(o, i) : make_int2(i, o);
+            }
+            s_pairs[pr] = ab;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const int m0 = mt * TILE_M, n0 = nt * NT;
+
+    if (warp < 4) {
+        // ============================ producers: gather both operands ============================
+        const int cc = lane & 7;     // 16-byte chunk inside a 32-channel atom
+        const int rsub = lane >> 3;  // pair inside a group of 4
+        const int a_ch = m0 + (warp * 8 + cc) * 4;
+        const bool a_ch_ok = a_ch < p.Cs;
+        for (int it = 0; it < n_items; it++) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(s_empty + s, ph ^ 1u);
+            const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t b_base = a_base + A_BYTES;
+            const int2 *pairs = s_pairs + it * WG_KR;
+            // A: warp w owns channel atom w; 8 instructions x (4 pairs x 128 B)
+#pragma unroll
+            for (int i = 0; i < WG_KR / 4; i++) {
+                const int r = 4 * i + rsub;
+                const int arow = pairs[r].x;
+                const bool ok = arow >= 0 && a_ch_ok;
+                const float *src = p.X + (int64_t)(ok ? arow : 0) * p.Cs + (ok ? a_ch : 0);
+                cp_async16(a_base + warp * WG_ATOM + r * 128 + swz_chunk(cc, r) * 16, src, ok ? 16u : 0u);
+            }
+            // B: warp w owns channel atoms w, w+4, ...
+            for (int atom = warp; atom < n_batoms; atom += 4) {
+                const int ch = (atom * 8 + cc) * 4;
+                const bool ch_ok = ch < NT;
+#pragma unroll
+                for (int i = 0; i < WG_KR / 4; i++) {
+                    const int r = 4 * i + rsub;
+                    const int brow = pairs[r].y;
+                    const bool ok = brow >= 0 && ch_ok;
+                    const float *src = p.dY + (int64_t)(ok ? brow : 0) * p.Cd + n0 + (ok ? ch : 0);
+                    cp_async16(b_base + atom * WG_ATOM + r * 128 + swz_chunk(cc, r) * 16, src, ok ? 16u : 0u);
+                }
+            }
+            cp_async_mbar_arrive_noinc(s_full + s);
+        }
+        // ============================ epilogue: reduce the tile into dW[k] ============================
+        mbar_wait(s_accum, 0);
+        tc_fence_after();
+        const int ci = m0 + warp * 32 + lane;  // accumulator row (TMEM lane) = input channel
+        float *out = p.dW + ((int64_t)k * p.Cs + ci) * p.Cd + n0;
+        for (int c = 0; c < NT; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (ci < p.Cs) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + j), "f"(__uint_as_float(v[j])),
+                                 "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                 : "memory");
+            }
+        }
+    } else if (warp == 5) {
+        // ============================ MMA issuer ============================
+        const uint32_t idesc = make_idesc_tf32_mn(TILE_M, NT);
+        for (int it = 0; it < n_items; it++) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(s_full + s, ph);
+            tc_fence_after();
+            proxy_fence_async();
+            if (lane == 0) {
+                const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+                for (int g = 0; g < WG_KR / 8; g++) {
+                    const uint64_t ad = make_smem_desc_sw128_32b(a_base + g * 1024, WG_ATOM, 512);
+                    const uint64_t bd = make_smem_desc_sw128_32b(b_base + g * 1024, WG_ATOM, 512);
+                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                }
+                umma_commit(s_empty + s);
+                if (it == n_items - 1) umma_commit(s_accum);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 int pick_nt(int Cd) {
     const int tiles = (Cd + 255) / 256;
     if (Cd % tiles) return 0;
@@ -370,6 +551,39 @@ int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, in
         U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_fwd_tc_kernel<16><<<grid, NUM_THREADS, smem, st>>>(p);
     }
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+int u2_conv_wgrad_tc(const float *X, int32_t Cs, const float *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
+                     int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, cudaStream_t st) {
+    const int NT = pick_nt(Cd);
+    U2_CHECK_ARG(NT && Cs % 4 == 0 && K <= 32, "u2_conv_wgrad_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
+    U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)dY | (uintptr_t)dW) & 15) == 0, "u2_conv_wgrad_tc: pointers must be 16-byte aligned");
+    U2_CHECK_ARG((int64_t)K * ld < 0x7FFFFFFFLL, "u2_conv_wgrad_tc: table too large for int32 flat indices");
+    U2_CUDA_OK(cudaMemsetAsync(dW, 0, (size_t)K * Cs * Cd * sizeof(float), st));
+    if (n_rows == 0) return 0;
+    WgradParams p;
+    p.X = X; p.dY = dY; p.nbr = nbr; p.flat = flat; p.nbsizes = nbsizes; p.dW = dW;
+    p.ld = ld; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT; p.swap = swap;
+    p.n_mt = (Cs + TILE_M - 1) / TILE_M;
+    p.n_nt = Cd / NT;
+    int cols = 32;
+    while (cols < NT) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = (size_t)(4 + (NT + 31) / 32) * WG_ATOM;
+    const size_t fixed = (size_t)WG_PAIRS * sizeof(int2) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
+    const size_t budget = 227 * 1024;
+    int stages = (int)((budget / 2 - fixed - 1024) / stage_bytes);
+    if (stages < 3) stages = (int)((budget - fixed) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    U2_CHECK_ARG(stages >= 2, "u2_conv_wgrad_tc: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + fixed;
+    // a single offset has at most n_rows pairs (one per row of the table's row side)
+    dim3 grid((unsigned)u2_ceil_div(n_rows, WG_PAIRS), (unsigned)K, (unsigned)(p.n_mt * p.n_nt));
+    U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_wgrad_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(p);
     U2_LAUNCH_OK();
     return 0;
 }

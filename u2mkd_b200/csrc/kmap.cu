@@ -164,3 +164,30 @@ extern "C" int u2_kmap_build(const int32_t *in_coords, int64_t n_in, const int32
     U2_LAUNCH_OK();
     return 0;
 }
+
+// ------------------------------------------------------------------ compacted pair list
+// flat[j] = k*ld + out_row of the j-th valid entry of nbr, ascending: the reference's
+// (k, out)-ordered nbmaps without the host-side nonzero(); consumed by the wgrad kernels.
+struct U2ValidEntry {
+    const int *nbr;
+    __device__ __forceinline__ bool operator()(const int &f) const { return nbr[f] >= 0; }
+};
+
+extern "C" size_t u2_kmap_pairs_scratch_bytes(int64_t total) {
+    size_t b = 0;
+    cub::DeviceSelect::If(nullptr, b, cub::CountingInputIterator<int>(0), (int *)nullptr, (int *)nullptr, (int)total,
+                          U2ValidEntry{nullptr});
+    return align_up(b) + 256;
+}
+
+extern "C" int u2_kmap_pairs(const int32_t *nbr, int64_t total, int32_t *flat, void *scratch, size_t scratch_bytes,
+                             u2_stream_t stream) {
+    U2_CHECK_ARG(total < 0x7FFFFFFFLL, "u2_kmap_pairs: table too large");
+    U2_CHECK_ARG(scratch_bytes >= u2_kmap_pairs_scratch_bytes(total), "u2_kmap_pairs: scratch too small");
+    if (total == 0) return 0;
+    int *n_sel = (int *)scratch;
+    size_t cub_bytes = scratch_bytes - 256;
+    U2_CUDA_OK(cub::DeviceSelect::If((char *)scratch + 256, cub_bytes, cub::CountingInputIterator<int>(0), flat, n_sel,
+                                     (int)total, U2ValidEntry{nbr}, (cudaStream_t)stream));
+    return 0;
+}

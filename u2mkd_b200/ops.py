@@ -232,6 +232,23 @@ class KernelMap:
         self.n_in, self.n_out = n_in, n_out
         self.K = nbr.shape[0]
         self._nbmaps = None
+        self._flat = None
+
+    @property
+    def flat_pairs(self) -> torch.Tensor:
+        """int32 flat indices k*ld_out + out_row of the valid entries of nbr, ascending (device-side
+        compaction, no host sync; sized for the worst case, valid prefix = nbsizes.sum())."""
+        if self._flat is None:
+            total = self.nbr.numel()
+            # a submanifold / strided map has at most min(K * n_out, K * n_in) pairs
+            cap = self.K * min(self.n_out, self.n_in) if self.K * min(self.n_out, self.n_in) > 0 else 1
+            flat = torch.empty(cap, dtype=torch.int, device=self.nbr.device)
+            sbytes = lib().u2_kmap_pairs_scratch_bytes(total)
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=self.nbr.device)
+            check(lib().u2_kmap_pairs(self.nbr.data_ptr(), total, flat.data_ptr(), scratch.data_ptr(), sbytes, _st()))
+            _count()
+            self._flat = flat
+        return self._flat
 
     @property
     def nbmaps(self) -> torch.Tensor:
@@ -345,7 +362,13 @@ class ConvolutionFn(Function):
             bwd_table = kmap.nbr if transposed else kmap.nbrT
             grad_feats = _conv_gather_gemm("dgrad", kmap, g, weight, True, bwd_table, feats.shape[0], cin,
                                            math).to(in_dtype)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, math):
+            grad_weight = torch.empty_like(weight)
+            flat = kmap.flat_pairs
+            _timed("wgrad", kmap, g.shape[0], K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                feats.data_ptr(), cin, g.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
+                flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), math, _st())))
+        elif ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
             n_dst = g.shape[0]
             sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, math)
