@@ -106,3 +106,23 @@ def test_spvcnn_tf32_vs_oracle(tc, oracle):
     assert rel_err(out_g, out_o) < TF32_REL
     ga, go = net_g.stem[3].kernel.grad, net_o.stem[3].kernel.grad
     assert rel_err(ga, go) < 0.15  # stem gradient after 48 tf32 layers back-to-back (per-op bar is 2e-2)
+
+
+def test_sorted_tiles_do_not_change_results(tc, oracle):
+    """The mask-sorted tile order only regroups rows into tiles: bitwise identical outputs."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(5)
+    c = rand_coords(rng, 9000, extent=40).cuda()
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], 64)).astype(np.float32)).cuda()
+    conv = gts.nn.Conv3d(64, 96, 3).cuda()
+    tc.set_math("tf32")
+    outs = []
+    for flag in (False, True):
+        tc.set_sort_tiles(flag)
+        x = gts.SparseTensor(f.clone().requires_grad_(True), c)
+        y = conv(x)
+        y.F.sum().backward()
+        outs.append((y.F.detach().clone(), x.F.grad.clone()))
+    tc.set_sort_tiles(True)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])

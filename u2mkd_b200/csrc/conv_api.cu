@@ -10,8 +10,8 @@ int u2_conv_wgrad_simt(const float *X, int64_t n_src, int32_t Cs, const float *d
 size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math);
 int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
-                   int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
-                   size_t scratch_bytes, cudaStream_t st);
+                   const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
+                   void *scratch, size_t scratch_bytes, cudaStream_t st);
 int u2_conv_wgrad_tc(const float *X, int32_t Cs, const float *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
                      int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, cudaStream_t st);
 #endif
@@ -48,7 +48,7 @@ extern "C" int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const floa
     if (math == U2_MATH_FP32) return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #ifdef U2_WITH_TC
     if (math == U2_MATH_TF32 && u2_conv_tc_supported(Cs, Cd, K, math))
-        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, st);
+        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, nullptr, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, st);
     if (math == U2_MATH_TF32)  // shapes the MMA tiles cannot hold (e.g. the Cs = 4 stem conv)
         return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #endif
@@ -91,5 +91,29 @@ extern "C" int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb
 #else
     u2_set_error("u2_conv_wgrad_pairs: built without the tcgen05 path");
     return 1;
+#endif
+}
+
+extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
+                                const int32_t *tableP, const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd,
+                                float *Y, int32_t math, void *scratch, size_t scratch_bytes, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    if (check_common(X, W, tableP, Y, Cs, Cd, K, ld, n_dst, "u2_conv_fwd_perm")) return 1;
+    U2_CHECK_ARG(perm != nullptr, "u2_conv_fwd_perm: null perm");
+    U2_CHECK_ARG(math == U2_MATH_TF32 && u2_conv_tc_supported(Cs, Cd, K, math), "u2_conv_fwd_perm: unsupported shape/math");
+    return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
+                          (cudaStream_t)stream);
+#else
+    u2_set_error("u2_conv_fwd_perm: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+extern "C" int u2_conv_tc_shape_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math) {
+#ifdef U2_WITH_TC
+    return u2_conv_tc_supported(Cs, Cd, K, math);
+#else
+    (void)Cs; (void)Cd; (void)K; (void)math;
+    return 0;
 #endif
 }

@@ -127,8 +127,9 @@ constexpr int A_LBO = A_ROW_GROUP + 16;       // +16: bank-conflict-free 16-byte
 
 struct FwdParams {
     const float *X;
-    const float *Wt;  // pre-tiled weights
-    const int *table;
+    const float *Wt;   // pre-tiled weights
+    const int *table;  // [K, ld] source row per (offset, tile row), -1 = none
+    const int *perm;   // tile row -> destination row (mask-sorted tiles), or nullptr = identity
     float *Y;
     int64_t ld, n_dst;
     int Cs, Cd, K, NT, stages, tmem_cols;
@@ -136,7 +137,8 @@ struct FwdParams {
 
 template <int KC>
 __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParams p) {
-    constexpr int CHUNKS = KC / 4;  // 16-byte chunks per row per stage
+    constexpr int CHUNKS = KC / 4;            // 16-byte chunks per row per stage
+    constexpr int ROWS_PER_IT = TILE_M / CHUNKS;  // rows covered by one cp.async round of the 128 producers
     constexpr int A_BYTES = CHUNKS * A_LBO;
     extern __shared__ __align__(128) uint8_t smem[];
     const int NT = p.NT;
@@ -192,72 +194,78 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
 
     if (warp < 4) {
         // ============================ A producers ============================
-        int it = 0;
+        const int chunk = tid % CHUNKS;
+        const uint32_t dst0 = (uint32_t)(chunk * A_LBO + (tid / CHUNKS) * 16);
+        int s = 0;
+        uint32_t ph = 0;
         for (uint32_t m = kmask; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
-            const int *tab_k = s_tab + k * TILE_M;
-            for (int cc = 0; cc < n_cc; cc++, it++) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            const int *tab_k = s_tab + k * TILE_M + tid / CHUNKS;
+            // per-offset setup: element offset of this thread's 16-byte piece in each of its rows
+            uint32_t off[CHUNKS];
+#pragma unroll
+            for (int i = 0; i < CHUNKS; i++) {
+                const int src = tab_k[i * ROWS_PER_IT];
+                off[i] = src >= 0 ? (uint32_t)src * (uint32_t)p.Cs + (uint32_t)(chunk * 4) : 0xFFFFFFFFu;
+            }
+            const float *xc = p.X;
+            for (int cc = 0; cc < n_cc; cc++, xc += KC) {
                 mbar_wait(s_empty + s, ph ^ 1u);
-                const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
-                const float *xcol = p.X + cc * KC;
+                const uint32_t a_dst = smem_u32(s_stage + (size_t)s * stage_bytes) + dst0;
 #pragma unroll
                 for (int i = 0; i < CHUNKS; i++) {
-                    const int piece = i * TILE_M + tid;
-                    const int row = piece / CHUNKS, chunk = piece % CHUNKS;
-                    const int src = tab_k[row];
-                    const float *g = xcol + (int64_t)(src >= 0 ? src : 0) * p.Cs + chunk * 4;
-                    cp_async16(a_base + chunk * A_LBO + row * 16, g, src >= 0 ? 16u : 0u);
+                    const bool ok = off[i] != 0xFFFFFFFFu;
+                    cp_async16(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u);
                 }
                 cp_async_mbar_arrive_noinc(s_full + s);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
         // ============================ epilogue ============================
-        const int64_t row = row0 + warp * 32 + lane;
-        float *yrow = p.Y + row * p.Cd + nt * NT;
+        const int64_t trow = row0 + warp * 32 + lane;
+        int64_t row = trow;
+        if (p.perm) row = __ldg(p.perm + trow);
+        const bool live = row >= 0 && row < p.n_dst;
+        float *yrow = p.Y + (live ? row : 0) * p.Cd + nt * NT;
         if (n_items > 0) {
             mbar_wait(s_accum, 0);
             tc_fence_after();
-        }
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-            uint32_t v[16];
-            if (n_items > 0) {
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld_wait();
-            } else {
+                if (live) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = 0u;
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
             }
-            if (row < p.n_dst) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
+        } else if (live) {
+            for (int c0 = 0; c0 < NT; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
         }
     } else if (warp == 4) {
         // ============================ B producer ============================
         if (lane == 0) {
-            int it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (uint32_t m = kmask; m; m &= m - 1) {
                 const int k = __ffs(m) - 1;
-                for (int cc = 0; cc < n_cc; cc++, it++) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                for (int cc = 0; cc < n_cc; cc++) {
                     mbar_wait(s_empty + s, ph ^ 1u);
                     const uint32_t b_base = smem_u32(s_stage + (size_t)s * stage_bytes + A_BYTES);
                     const float *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(KC * NT);
                     mbar_arrive_expect_tx(s_full + s, (uint32_t)B_BYTES);
                     bulk_g2s(b_base, blob, (uint32_t)B_BYTES, s_full + s);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else {
         // ============================ MMA issuer ============================
         const uint32_t idesc = make_idesc_tf32(TILE_M, NT);
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < n_items; it++) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(s_full + s, ph);
             tc_fence_after();
             proxy_fence_async();
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                 if (it == n_items - 1) umma_commit(s_accum);
             }
             __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     }
     tc_fence_before();
@@ -508,9 +517,10 @@ size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd
 }
 
 int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
-                   int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
-                   size_t scratch_bytes, cudaStream_t st) {
-    (void)n_src; (void)math;
+                   const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
+                   void *scratch, size_t scratch_bytes, cudaStream_t st) {
+    (void)math;
+    U2_CHECK_ARG(n_src * (int64_t)Cs < 0xFFFFFFFFLL, "u2_conv_fwd_tc: source tensor too large for 32-bit element offsets");
     if (n_dst == 0) return 0;
     const int KC = pick_kc(Cs), NT = pick_nt(Cd);
     U2_CHECK_ARG(KC && NT && K <= 32, "u2_conv_fwd_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
@@ -526,7 +536,7 @@ int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, in
     U2_LAUNCH_OK();
 
     FwdParams p;
-    p.X = X; p.Wt = (const float *)scratch; p.table = table; p.Y = Y;
+    p.X = X; p.Wt = (const float *)scratch; p.table = table; p.perm = perm; p.Y = Y;
     p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
     int cols = 32;
     while (cols < NT) cols <<= 1;
@@ -543,7 +553,8 @@ int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, in
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     p.stages = stages;
     const size_t smem = stages * stage_bytes + fixed;
-    dim3 grid((unsigned)u2_ceil_div(n_dst, TILE_M), (unsigned)(Cd / NT));
+    // with a row permutation the tiles run over the (padded) table rows, destination rows come from perm
+    dim3 grid((unsigned)u2_ceil_div(perm ? ld : n_dst, TILE_M), (unsigned)(Cd / NT));
     if (KC == 32) {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_fwd_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(p);

@@ -191,3 +191,81 @@ extern "C" int u2_kmap_pairs(const int32_t *nbr, int64_t total, int32_t *flat, v
                                      (int)total, U2ValidEntry{nbr}, (cudaStream_t)stream));
     return 0;
 }
+
+// ------------------------------------------------------------------ mask-sorted tile order
+// The tensor-core conv walks 128-row tiles and, per tile, only the offsets that have at least
+// one neighbour in the tile.  Sorting the rows by their neighbour-presence mask (rare offsets
+// in the high bits) makes the rows of a tile agree on which offsets they use: ~2.7x fewer
+// (tile, offset) work items on LiDAR scans.  Rows keep their identity through `perm`
+// (tile row -> original row); results are written back to the original rows, so nothing
+// observable changes order.
+struct U2BitPos { int pos[32]; };
+
+__global__ void __launch_bounds__(256) rowkey_kernel(const int *__restrict__ tab, int64_t ld, int64_t n, int K, U2BitPos bp,
+                                                     unsigned long long *__restrict__ keys) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    unsigned int m = 0;
+    for (int k = 0; k < K; k++)
+        if (__ldg(tab + (int64_t)k * ld + r) >= 0) m |= 1u << bp.pos[k];
+    keys[r] = ((unsigned long long)m << 32) | (unsigned long long)r;
+}
+
+__global__ void __launch_bounds__(256) perm_from_keys_kernel(const unsigned long long *__restrict__ keys, int64_t n, int64_t ld,
+                                                             int *__restrict__ perm) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ld) return;
+    perm[j] = j < n ? (int)(keys[j] & 0xFFFFFFFFull) : -1;
+}
+
+__global__ void __launch_bounds__(256) permute_table_kernel(const int *__restrict__ tab, int64_t ld, int K,
+                                                            const int *__restrict__ perm, int *__restrict__ tabP) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ld) return;
+    const int r = __ldg(perm + j);
+    const int k = blockIdx.y;
+    tabP[(int64_t)k * ld + j] = r >= 0 ? __ldg(tab + (int64_t)k * ld + r) : -1;
+}
+
+static size_t sort_cub_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, n, 32, 64);
+    return align_up(b);
+}
+
+extern "C" size_t u2_kmap_sort_scratch_bytes(int64_t n_rows) {
+    if (n_rows <= 0) n_rows = 1;
+    return 2 * align_up((size_t)n_rows * 8) + sort_cub_bytes(n_rows);
+}
+
+extern "C" int u2_kmap_sort_rows(const int32_t *table, int64_t ld, int64_t n_rows, int32_t K, const int32_t *bitpos_host,
+                                 const int32_t *perm_in, int32_t *perm_out, int32_t *tableP, void *scratch,
+                                 size_t scratch_bytes, u2_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    U2_CHECK_ARG(K > 0 && K <= 32, "u2_kmap_sort_rows: K=%d (needs 1..32)", K);
+    U2_CHECK_ARG(ld >= n_rows && n_rows < 0x7FFFFFFFLL, "u2_kmap_sort_rows: bad sizes");
+    if (ld == 0) return 0;
+    const unsigned grid_ld = (unsigned)u2_ceil_div(ld, 256);
+    const int *perm = perm_in;
+    if (perm_in == nullptr) {
+        U2_CHECK_ARG(scratch_bytes >= u2_kmap_sort_scratch_bytes(n_rows), "u2_kmap_sort_rows: scratch too small");
+        U2BitPos bp;
+        for (int k = 0; k < 32; k++) bp.pos[k] = k < K ? bitpos_host[k] : 0;
+        for (int k = 0; k < K; k++) U2_CHECK_ARG(bp.pos[k] >= 0 && bp.pos[k] < 32, "u2_kmap_sort_rows: bad bit position");
+        char *p = (char *)scratch;
+        unsigned long long *keys_a = (unsigned long long *)p; p += align_up((size_t)(n_rows > 0 ? n_rows : 1) * 8);
+        unsigned long long *keys_b = (unsigned long long *)p; p += align_up((size_t)(n_rows > 0 ? n_rows : 1) * 8);
+        if (n_rows > 0) {
+            rowkey_kernel<<<(unsigned)u2_ceil_div(n_rows, 256), 256, 0, st>>>(table, ld, n_rows, K, bp, keys_a);
+            U2_LAUNCH_OK();
+            size_t cub_bytes = sort_cub_bytes(n_rows);
+            U2_CUDA_OK(cub::DeviceRadixSort::SortKeys(p, cub_bytes, keys_a, keys_b, n_rows, 32, 32 + K, st));
+        }
+        perm_from_keys_kernel<<<grid_ld, 256, 0, st>>>(keys_b, n_rows, ld, perm_out);
+        U2_LAUNCH_OK();
+        perm = perm_out;
+    }
+    permute_table_kernel<<<dim3(grid_ld, (unsigned)K), 256, 0, st>>>(table, ld, K, perm, tableP);
+    U2_LAUNCH_OK();
+    return 0;
+}

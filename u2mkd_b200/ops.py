@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
 
 _MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
-_state = {"math": MATH_FP32}
+_state = {"math": MATH_FP32, "sort_tiles": True}
 
 # instrumentation used by bench.py: number of kernels this library launched, and an optional
 # per-launch CUDA-event timer for the conv kernels (the dominant kernel of the path)
@@ -36,6 +36,11 @@ def set_math(mode: str) -> None:
     if m != MATH_FP32 and not lib().u2_has_tensor_core_path():
         raise RuntimeError("this build of libu2mkd_b200.so has no tcgen05 conv path")
     _state["math"] = m
+
+
+def set_sort_tiles(flag: bool) -> None:
+    """Mask-sorted tile order for the tensor-core conv (on by default)."""
+    _state["sort_tiles"] = bool(flag)
 
 
 def get_math() -> str:
@@ -227,12 +232,53 @@ class KernelMap:
     [nbmaps int64 [M,2] rows (in, out) ordered by (k, out), nbsizes [K], (N_in, N_out)].
     """
 
-    def __init__(self, nbr, nbrT, nbsizes, n_in, n_out):
+    def __init__(self, nbr, nbrT, nbsizes, n_in, n_out, offsets_host=None, same_coords=False):
         self.nbr, self.nbrT, self.nbsizes = nbr, nbrT, nbsizes
         self.n_in, self.n_out = n_in, n_out
         self.K = nbr.shape[0]
+        self.offsets_host = offsets_host  # [K][3] python ints (host), for the sort key layout
+        self.same_coords = same_coords    # submanifold map: input and output rows are the same voxels
         self._nbmaps = None
         self._flat = None
+        self._sorted = {}
+
+    def _bitpos(self):
+        """Bit of each offset in the row sort key: rare offsets (corners, then edges, vertical
+        before horizontal) in the high bits, the always-present centre lowest."""
+        K = self.K
+        offs = self.offsets_host if self.offsets_host is not None else [[0, 0, 0]] * K
+        order = sorted(range(K), key=lambda k: (sum(1 for v in offs[k] if v != 0), offs[k][2] != 0, k))
+        pos = [0] * K
+        for rank, k in enumerate(order):
+            pos[k] = rank
+        return (ctypes.c_int32 * K)(*pos)
+
+    def sorted_tables(self, transposed_side: bool):
+        """(tableP [K, ld], perm [ld]) for the tensor-core conv: rows sorted by neighbour mask.
+        transposed_side=False: the nbr table (rows = output voxels); True: nbrT (rows = input voxels)."""
+        key = bool(transposed_side)
+        if key not in self._sorted:
+            table = self.nbrT if key else self.nbr
+            n_rows = self.n_in if key else self.n_out
+            ld = table.shape[1]
+            tabP = torch.empty_like(table)
+            other = self._sorted.get(not key)
+            st = _st()
+            if self.same_coords and other is not None:
+                # nbrT[k][i] == nbr[K-1-k][i] on a submanifold map: the same row order is as good
+                perm = other[1]
+                check(lib().u2_kmap_sort_rows(table.data_ptr(), ld, n_rows, self.K, None, perm.data_ptr(), None,
+                                              tabP.data_ptr(), None, 0, st))
+                _count(1)
+            else:
+                perm = torch.empty(ld, dtype=torch.int, device=table.device)
+                sbytes = lib().u2_kmap_sort_scratch_bytes(n_rows)
+                scratch = torch.empty(sbytes, dtype=torch.uint8, device=table.device)
+                check(lib().u2_kmap_sort_rows(table.data_ptr(), ld, n_rows, self.K, self._bitpos(), None, perm.data_ptr(),
+                                              tabP.data_ptr(), scratch.data_ptr(), sbytes, st))
+                _count(7)
+            self._sorted[key] = (tabP, perm)
+        return self._sorted[key]
 
     @property
     def flat_pairs(self) -> torch.Tensor:
@@ -280,9 +326,13 @@ def _pad(n: int) -> int:
     return max(_PAD, (n + _PAD - 1) // _PAD * _PAD)
 
 
-def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets: torch.Tensor) -> KernelMap:
+def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets: torch.Tensor,
+                     offsets_host=None) -> KernelMap:
     """For every output voxel o and offset k: the input voxel at coord(o) + offset_k."""
     _need_cuda(in_coords, out_coords, offsets)
+    same = in_coords is out_coords
+    if offsets_host is None:
+        offsets_host = offsets.cpu().tolist()
     in_coords = in_coords.contiguous()
     out_coords = out_coords.contiguous()
     offsets = offsets.contiguous().int()
@@ -298,7 +348,7 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets:
                               nbr.data_ptr(), ld_out, nbrT.data_ptr(), ld_in, nbsizes.data_ptr(), scratch.data_ptr(),
                               sbytes, _st()))
     _count(2)
-    return KernelMap(nbr, nbrT, nbsizes, n_in, n_out)
+    return KernelMap(nbr, nbrT, nbsizes, n_in, n_out, offsets_host, same)
 
 
 # -------------------------------------------------------------------------------- convolution
@@ -315,12 +365,18 @@ def _timed(kind, kmap, n_dst, K, c_src, c_dst, launch):
     conv_timer.record(kind, kmap, n_dst, K, c_src, c_dst, e0, e1)
 
 
-def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math):
+def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math, side=None):
     K, ld = table.shape
     n_src, c_src = x.shape
     y = torch.empty((n_dst, c_dst), dtype=torch.float32, device=x.device)
     sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device) if sbytes else None
+    if side is not None and _state["sort_tiles"] and lib().u2_conv_tc_shape_supported(c_src, c_dst, K, math):
+        tabP, perm = kmap.sorted_tables(side)
+        _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd_perm(
+            x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), tabP.data_ptr(), perm.data_ptr(), ld, n_dst, K,
+            c_dst, y.data_ptr(), math, _ptr(scratch), sbytes, _st())))
+        return y
     _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd(
         x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
         math, _ptr(scratch), sbytes, _st())))
@@ -345,7 +401,7 @@ class ConvolutionFn(Function):
         else:
             table, n_dst = kmap.nbrT, kmap.n_in
             assert feats.shape[0] == kmap.n_out, (feats.shape, kmap.sizes)
-        out = _conv_gather_gemm("fwd", kmap, feats, weight, False, table, n_dst, cout, math)
+        out = _conv_gather_gemm("fwd", kmap, feats, weight, False, table, n_dst, cout, math, side=bool(transposed))
         ctx.save_for_backward(feats, weight)
         ctx.misc = (kmap, transposed, math, in_dtype)
         return out.to(in_dtype)
@@ -360,8 +416,8 @@ class ConvolutionFn(Function):
         fwd_table = kmap.nbrT if transposed else kmap.nbr
         if ctx.needs_input_grad[0]:
             bwd_table = kmap.nbr if transposed else kmap.nbrT
-            grad_feats = _conv_gather_gemm("dgrad", kmap, g, weight, True, bwd_table, feats.shape[0], cin,
-                                           math).to(in_dtype)
+            grad_feats = _conv_gather_gemm("dgrad", kmap, g, weight, True, bwd_table, feats.shape[0], cin, math,
+                                           side=not transposed).to(in_dtype)
         if ctx.needs_input_grad[1] and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, math):
             grad_weight = torch.empty_like(weight)
             flat = kmap.flat_pairs

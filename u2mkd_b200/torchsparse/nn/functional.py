@@ -9,7 +9,7 @@ from ... import ops
 from ...ops import calc_ti_weights, spcount, spdevoxelize, sphash, sphashquery, spvoxelize
 from ..tensor import SparseTensor
 from ..utils import make_ntuple
-from .utils import get_kernel_offsets
+from .utils import get_kernel_offsets, kernel_offsets_host
 
 __all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "spdownsample",
            "conv3d"]
@@ -52,7 +52,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
             offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=feats.device)
             if any(s > 1 for s in stride):
                 coords = spdownsample(coords, stride, kernel_size, input.stride)
-            kmap = ops.build_kernel_map(input.coords, coords, offsets)
+            kmap = ops.build_kernel_map(input.coords, coords, offsets, kernel_offsets_host(kernel_size, input.stride))
             input.kmaps[key] = kmap
         elif any(s > 1 for s in stride):
             coords = input.cmaps[out_stride]  # upstream skips this on a cache hit
