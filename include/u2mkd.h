@@ -166,6 +166,23 @@ int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, 
                      const int32_t *tableP, const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd,
                      float *Y, int32_t math, void *scratch, size_t scratch_bytes, u2_stream_t stream);
 
+/* ---- BatchNorm (+ fused ReLU) over feature matrices fp32 [n, C], training mode: what the reference runs as
+ * torch BatchNorm1d / SyncBatchNorm + ReLU on SparseTensor.F after every conv
+ * (core/models/build_blocks.py:21-84, core/models/utils.py:138-141); SURVEY.md §8(f)-2.
+ * sums fp64 [2C+1] = (sum x, sum x^2, row count) — all-reduce it across ranks for SyncBatchNorm, then
+ * u2_bn_apply derives mean / invstd (written to save_mean / save_invstd, running stats updated if non-NULL).
+ * backward: dsum fp64 [2C] = (sum dz, sum dz*xhat) = (grad beta, grad gamma); all-reduce a copy for dx.    */
+int u2_bn_supported(int32_t C);
+int u2_bn_stats(const float *x, int64_t n, int32_t C, double *sums, u2_stream_t stream);
+int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
+                const float *gamma, const float *beta, int32_t relu, float *y, float *save_mean, float *save_invstd,
+                float *running_mean, float *running_var, u2_stream_t stream);
+int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
+                     const float *gamma, const float *beta, int32_t relu, double *dsum, u2_stream_t stream);
+int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
+                    const float *gamma, const float *beta, const double *dsum, const double *count_dev, int32_t relu,
+                    float *dx, u2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,15 +79,15 @@ def main():
     km = ops.build_kernel_map(c, c, get_kernel_offsets(3, 1, 1, device="cuda"))
     M = int(km.nbsizes.sum())
     if args.only in ("all", "conv"):
-        for cin, cout in ((64, 64), (128, 128), (256, 192)):
+        for cin, cout in ((64, 64), (128, 128), (256, 192), (192, 192)):
             x = torch.randn(n, cin, device="cuda")
             w = torch.randn(27, cin, cout, device="cuda") * 0.05
             g = torch.randn(n, cout, device="cuda")
             fl = 2.0 * M * cin * cout
             by = (n * cin + n * cout + 27 * cin * cout) * 4 + 4 * 27 * n
-            report(f"conv_fwd k3 {cin}->{cout} n={n} M={M}", timeit(lambda: ops._conv_gather_gemm("fwd", km, x, w, False, km.nbr, n, cout, ops._state["math"]), args.reps),
+            report(f"conv_fwd k3 {cin}->{cout} n={n} M={M}", timeit(lambda: ops._conv_gather_gemm("fwd", km, x, w, False, km.nbr, n, cout, ops._state["math"], side=False), args.reps),
                    bytes_=by, flops=fl)
-            report(f"conv_dgrad k3 {cout}->{cin}", timeit(lambda: ops._conv_gather_gemm("dgrad", km, g, w, True, km.nbrT, n, cin, ops._state["math"]), args.reps),
+            report(f"conv_dgrad k3 {cout}->{cin}", timeit(lambda: ops._conv_gather_gemm("dgrad", km, g, w, True, km.nbrT, n, cin, ops._state["math"], side=True), args.reps),
                    bytes_=by, flops=fl)
             flat = km.flat_pairs
             dw = torch.empty_like(w)

@@ -12,6 +12,8 @@ torch.backends.cuda.matmul.allow_tf32 = math != "fp32"
 w = scans.WORKLOADS["nusc5_cr2.0_b2"]
 dev = torch.device("cuda")
 net = models.product().SPVCNN(cr=w["cr"], pres=w["voxel_size"], vres=w["voxel_size"]).to(dev)
+from u2mkd_b200 import fusion
+if "--no-fusion" not in sys.argv: fusion.optimize(net)
 opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)
 pool = []
 for i in range(2):

@@ -280,3 +280,54 @@ def test_cpu_tensor_is_rejected(gpu):
     c = torch.zeros((4, 4), dtype=torch.int)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gpu.sphash(c)
+
+
+# ---------------------------------------------------------------- fused BatchNorm(+ReLU)
+@pytest.mark.parametrize("n,c,relu", [(5000, 64, True), (777, 192, False), (3000, 16, True), (100, 768, True), (2, 32, False)])
+def test_batch_norm_relu_kernels(gpu, n, c, relu):
+    from u2mkd_b200 import ops
+    torch.manual_seed(n + c)
+    x = (torch.randn(n, c, device="cuda") * 3 + 5)
+    bn_a, bn_b = torch.nn.BatchNorm1d(c).cuda(), torch.nn.BatchNorm1d(c).cuda()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5); bn_a.bias.uniform_(-0.5, 0.5)
+    bn_b.load_state_dict(bn_a.state_dict())
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = ops.batch_norm_relu(xa, bn_a, relu=relu)
+    yb = bn_b(xb)
+    yb = torch.relu(yb) if relu else yb
+    assert rel_err(ya, yb) < FP32_REL
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    if n > 1:
+        assert rel_err(xa.grad, xb.grad) < 5e-4
+        assert rel_err(bn_a.weight.grad, bn_b.weight.grad) < 5e-4
+    assert rel_err(bn_a.bias.grad, bn_b.bias.grad) < 5e-4
+    assert rel_err(bn_a.running_mean, bn_b.running_mean) < 1e-5
+    if n > 1:
+        assert rel_err(bn_a.running_var, bn_b.running_var) < 1e-4
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 1
+
+
+def test_fusion_pass_keeps_model_function(gpu, oracle):
+    from u2mkd_b200 import fusion, models, scans
+    import u2mkd_b200.torchsparse as gts
+    coords, feats = scans.make_batch([5], "nusc", 1, 0.2)
+    torch.manual_seed(0)
+    fam = models.product()
+    net_a = fam.SPVCNN(cr=0.5, pres=0.2, vres=0.2).cuda()
+    net_b = fam.SPVCNN(cr=0.5, pres=0.2, vres=0.2).cuda()
+    net_b.load_state_dict(net_a.state_dict())
+    keys = list(net_b.state_dict().keys())
+    fusion.optimize(net_b)
+    assert list(net_b.state_dict().keys()) == keys
+    net_a.dropout = net_b.dropout = torch.nn.Identity()
+    outs = []
+    for net in (net_a, net_b):
+        x = gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())
+        out = net({"lidar": x})["x_vox"]
+        out.square().mean().backward()
+        outs.append((out.detach(), net.stem[3].kernel.grad.clone(), net.vox_ups[0][1][0].net[0].kernel.grad.clone()))
+    for a, b in zip(*outs):
+        assert rel_err(b, a) < 1e-3

@@ -133,6 +133,7 @@ struct FwdParams {
     float *Y;
     int64_t ld, n_dst;
     int Cs, Cd, K, NT, stages, tmem_cols;
+    long long *dbg;  // optional per-CTA phase timestamps (U2_DEBUG_CONV_TIMING)
 };
 
 template <int KC>
@@ -156,6 +157,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
     const int nt = blockIdx.y;
+    long long *dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && tid == 0) dbg[0] = clock64();
     const int n_cc = p.Cs / KC;
     const int n_nt = p.Cd / NT;
 
@@ -173,17 +176,31 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         tmem_relinquish();
     }
     __syncthreads();
-    // neighbour table of this tile -> smem, and the set of offsets that have any neighbour
-    for (int k = warp; k < p.K; k += NUM_THREADS / 32) {
-        bool any = false;
+    // neighbour table of this tile -> smem, and the set of offsets that have any neighbour.
+    // All loads of a thread are issued before the first use (one L2 round trip, not K/6 of them).
+    {
+        constexpr int MAXJ = 6;  // ceil(32 / 6 warps)
+        int v[MAXJ][TILE_M / 32];
 #pragma unroll
-        for (int j = 0; j < TILE_M / 32; j++) {
-            const int r = lane + 32 * j;
-            const int v = __ldg(p.table + (int64_t)k * p.ld + row0 + r);
-            s_tab[k * TILE_M + r] = v;
-            any |= v >= 0;
+        for (int j = 0; j < MAXJ; j++) {
+            const int k = warp + j * (NUM_THREADS / 32);
+#pragma unroll
+            for (int i = 0; i < TILE_M / 32; i++)
+                v[j][i] = k < p.K ? __ldg(p.table + (int64_t)k * p.ld + row0 + lane + 32 * i) : -1;
         }
-        if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(s_mask, 1u << k);
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++) {
+            const int k = warp + j * (NUM_THREADS / 32);
+            if (k < p.K) {
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < TILE_M / 32; i++) {
+                    s_tab[k * TILE_M + lane + 32 * i] = v[j][i];
+                    any |= v[j][i] >= 0;
+                }
+                if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(s_mask, 1u << k);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -191,6 +208,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     const uint32_t kmask = *s_mask;
     const uint32_t tmem_base = *s_tmem;
     const int n_items = __popc(kmask) * n_cc;
+    if (dbg && tid == 0) { dbg[1] = clock64(); dbg[6] = n_items; }
 
     if (warp < 4) {
         // ============================ A producers ============================
@@ -222,6 +240,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             }
         }
         // ============================ epilogue ============================
+        if (dbg && tid == 0) dbg[2] = clock64();
         const int64_t trow = row0 + warp * 32 + lane;
         int64_t row = trow;
         if (p.perm) row = __ldg(p.perm + trow);
@@ -230,9 +249,30 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         if (n_items > 0) {
             mbar_wait(s_accum, 0);
             tc_fence_after();
-            for (int c0 = 0; c0 < NT; c0 += 16) {
+            if (dbg && tid == 0) dbg[3] = clock64();
+            // 64 accumulator columns per round: four tcgen05.ld in flight, one wait
+            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+            int c0 = 0;
+            for (; c0 + 64 <= NT; c0 += 64) {
+                uint32_t v0[16], v1[16], v2[16], v3[16];
+                tmem_ld16(t_row + (uint32_t)c0, v0);
+                tmem_ld16(t_row + (uint32_t)c0 + 16, v1);
+                tmem_ld16(t_row + (uint32_t)c0 + 32, v2);
+                tmem_ld16(t_row + (uint32_t)c0 + 48, v3);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                        *reinterpret_cast<uint4 *>(yrow + c0 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+                        *reinterpret_cast<uint4 *>(yrow + c0 + 32 + j) = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+                        *reinterpret_cast<uint4 *>(yrow + c0 + 48 + j) = make_uint4(v3[j], v3[j + 1], v3[j + 2], v3[j + 3]);
+                    }
+                }
+            }
+            for (; c0 < NT; c0 += 16) {
                 uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld16(t_row + (uint32_t)c0, v);
                 tmem_ld_wait();
                 if (live) {
 #pragma unroll
@@ -285,9 +325,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     }
+    if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (dbg && tid == 160) { dbg[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
 }
 
 // W [K][Cs][Cd] (or [K][Cd][Cs] if WT) -> blobs [k][cc][nt][chunk][n][4] in UMMA K-major layout
@@ -537,6 +579,9 @@ int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, in
 
     FwdParams p;
     p.X = X; p.Wt = (const float *)scratch; p.table = table; p.perm = perm; p.Y = Y;
+    static long long *g_dbg = nullptr;
+    if (getenv("U2_DEBUG_CONV_TIMING") && !g_dbg) cudaMalloc(&g_dbg, (size_t)8 * 8 * 65536);
+    p.dbg = g_dbg;
     p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
     int cols = 32;
     while (cols < NT) cols <<= 1;
@@ -563,6 +608,22 @@ int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, in
         conv_fwd_tc_kernel<16><<<grid, NUM_THREADS, smem, st>>>(p);
     }
     U2_LAUNCH_OK();
+    if (g_dbg) {
+        const int nb = (int)(grid.x * grid.y) < 65536 ? (int)(grid.x * grid.y) : 65536;
+        long long *h = (long long *)malloc((size_t)nb * 64);
+        cudaMemcpy(h, g_dbg, (size_t)nb * 64, cudaMemcpyDeviceToHost);
+        double pro = 0, prod = 0, mma_tail = 0, epi = 0, tot = 0, items = 0;
+        long long tmin = h[0], tmax = 0;
+        for (int b = 0; b < nb; b++) {
+            long long *d = h + b * 8;
+            pro += d[1] - d[0]; prod += d[2] - d[1]; mma_tail += d[3] - d[2]; epi += d[4] - d[3]; tot += d[5] - d[0]; items += d[6];
+            if (d[0] < tmin) tmin = d[0];
+            if (d[5] > tmax) tmax = d[5];
+        }
+        printf("[conv timing] Cs=%d Cd=%d NT=%d stages=%d ctas=%d smem=%zu | avg cycles/CTA: prologue %.0f, produce %.0f, wait-accum %.0f, epilogue %.0f, total %.0f | items/CTA %.1f -> %.0f cyc/item\n",
+               Cs, Cd, NT, stages, nb, smem, pro / nb, prod / nb, mma_tail / nb, epi / nb, tot / nb, items / nb, prod / (items > 0 ? items : 1));
+        free(h);
+    }
     return 0;
 }
 

@@ -437,3 +437,71 @@ class ConvolutionFn(Function):
 
 def sparse_conv(feats, weight, kmap: KernelMap, transposed: bool = False, math: Optional[int] = None):
     return ConvolutionFn.apply(feats, weight, kmap, transposed, _state["math"] if math is None else math)
+
+
+# -------------------------------------------------------------------------------- batch norm (+ReLU)
+class BatchNormFn(Function):
+    """Training-mode BatchNorm over [n, C] features with an optional fused ReLU and an optional
+    process group (SyncBatchNorm semantics: statistics over the rows of all ranks)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, group):
+        _need_cuda(x, gamma, beta)
+        x = x.contiguous().float()
+        n, c = x.shape
+        st = _st()
+        sums = torch.empty(2 * c + 1, dtype=torch.float64, device=x.device)
+        check(lib().u2_bn_stats(x.data_ptr(), n, c, sums.data_ptr(), st))
+        if group is not None:
+            torch.distributed.all_reduce(sums, group=group)
+        y = torch.empty_like(x)
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        check(lib().u2_bn_apply(x.data_ptr(), n, c, sums.data_ptr(), float(eps), float(momentum), gamma.data_ptr(),
+                                beta.data_ptr(), int(relu), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                _ptr(running_mean), _ptr(running_var), _st()))
+        _count(3)
+        ctx.save_for_backward(x, gamma, beta, mean, invstd, sums)
+        ctx.misc = (relu, group)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, invstd, sums = ctx.saved_tensors
+        relu, group = ctx.misc
+        dy = dy.contiguous().float()
+        n, c = x.shape
+        st = _st()
+        dsum = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        check(lib().u2_bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), st))
+        dbeta, dgamma = dsum[:c].float(), dsum[c:].float()   # local sums: DDP averages parameter grads
+        if group is not None:
+            dsum = dsum.clone()
+            torch.distributed.all_reduce(dsum, group=group)
+        dx = torch.empty_like(x)
+        check(lib().u2_bn_bwd_apply(dy.data_ptr(), x.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                    beta.data_ptr(), dsum.data_ptr(), sums.data_ptr() + 16 * c, int(relu), dx.data_ptr(),
+                                    _st()))
+        _count(2)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def batch_norm_relu(x, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = False, group=None):
+    """BatchNorm(+ReLU) of a feature matrix with the module's parameters / running statistics.
+    Training mode on supported shapes runs the fused kernels; everything else falls back to torch's
+    batch_norm (eval mode, C not a multiple of 4, no affine)."""
+    c = x.shape[1]
+    if bn.training and x.shape[0] == 1 and group is None:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {x.size()}")
+    if (bn.training and x.is_cuda and bn.affine and x.dtype == torch.float32 and lib().u2_bn_supported(c)
+            and x.shape[0] > 0):
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        rm = bn.running_mean if bn.track_running_stats else None
+        rv = bn.running_var if bn.track_running_stats else None
+        return BatchNormFn.apply(x, bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu, group)
+    y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
+                                       0.1 if bn.momentum is None else bn.momentum, bn.eps)
+    return torch.relu(y) if relu else y

@@ -61,8 +61,11 @@ class Conv3d(nn.Module):
 
 
 class BatchNorm(nn.BatchNorm1d):
+    """BatchNorm1d over SparseTensor.F; training mode runs the kernels of csrc/norm.cu."""
+
     def forward(self, input: SparseTensor) -> SparseTensor:
-        return fapply(input, super().forward)
+        from ... import ops
+        return fapply(input, lambda f: ops.batch_norm_relu(f, self))
 
 
 class ReLU(nn.ReLU):
