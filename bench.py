@@ -100,15 +100,17 @@ class ConvTimer:
         self.items = []
 
     def record(self, kind, kmap, n_dst, K, c_src, c_dst, e0, e1):
-        self.items.append((kind, kmap, n_dst, K, c_src, c_dst, e0, e1))
+        # keep only the [K] pair-count tensor: holding the kernel map itself would pin ~100 MB of
+        # neighbour tables per step and push the caching allocator into cudaMalloc every step
+        self.items.append((kind, kmap.nbsizes, n_dst, K, c_src, c_dst, e0, e1))
 
     def summary(self):
         """per kind: launches, total ms, algorithmic flops (2*M*Cs*Cd over REAL pairs only)."""
         out, pairs_cache = {}, {}
-        for kind, kmap, n_dst, K, cs, cd, e0, e1 in self.items:
-            key = id(kmap)
+        for kind, nbsizes, n_dst, K, cs, cd, e0, e1 in self.items:
+            key = id(nbsizes)
             if key not in pairs_cache:
-                pairs_cache[key] = int(kmap.nbsizes.sum().item())
+                pairs_cache[key] = int(nbsizes.sum().item())
             d = out.setdefault(kind, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)

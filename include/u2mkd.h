@@ -156,15 +156,18 @@ int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb, int32_t C
  * each offset in the sort key (rare offsets high).  perm_in != NULL: reuse that permutation
  * (no sort), only permute `table`.  scratch from u2_kmap_sort_scratch_bytes(n_rows).            */
 size_t u2_kmap_sort_scratch_bytes(int64_t n_rows);
+/* tile_mask uint32 [ld/128] (may be NULL): bit k set iff 128-row tile j of tableP uses offset k. */
 int u2_kmap_sort_rows(const int32_t *table, int64_t ld, int64_t n_rows, int32_t K, const int32_t *bitpos_host,
-                      const int32_t *perm_in, int32_t *perm_out, int32_t *tableP, void *scratch,
+                      const int32_t *perm_in, int32_t *perm_out, int32_t *tableP, uint32_t *tile_mask, void *scratch,
                       size_t scratch_bytes, u2_stream_t stream);
 /* 1 if (Cs, Cd, K) runs on the tcgen05 kernels in this math mode (else the FFMA kernel is used) */
 int u2_conv_tc_shape_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
-/* u2_conv_fwd over a permuted table: tile row j reads table[k][j] and writes Y[perm[j], :]. */
+/* u2_conv_fwd over a permuted table: tile row j reads tableP[k][j] and writes Y[perm[j], :].
+ * tile_mask != NULL selects the multi-tile kernel (weights fetched once per up-to-4 tiles). */
 int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
-                     const int32_t *tableP, const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd,
-                     float *Y, int32_t math, void *scratch, size_t scratch_bytes, u2_stream_t stream);
+                     const int32_t *tableP, const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst,
+                     int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch, size_t scratch_bytes,
+                     u2_stream_t stream);
 
 /* ---- BatchNorm (+ fused ReLU) over feature matrices fp32 [n, C], training mode: what the reference runs as
  * torch BatchNorm1d / SyncBatchNorm + ReLU on SparseTensor.F after every conv

@@ -283,7 +283,7 @@ def test_cpu_tensor_is_rejected(gpu):
 
 
 # ---------------------------------------------------------------- fused BatchNorm(+ReLU)
-@pytest.mark.parametrize("n,c,relu", [(5000, 64, True), (777, 192, False), (3000, 16, True), (100, 768, True), (2, 32, False)])
+@pytest.mark.parametrize("n,c,relu", [(5000, 64, True), (777, 192, False), (3000, 16, True), (100, 768, True), (8, 32, False)])
 def test_batch_norm_relu_kernels(gpu, n, c, relu):
     from u2mkd_b200 import ops
     torch.manual_seed(n + c)

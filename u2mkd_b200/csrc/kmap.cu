@@ -227,6 +227,21 @@ __global__ void __launch_bounds__(256) permute_table_kernel(const int *__restric
     tabP[(int64_t)k * ld + j] = r >= 0 ? __ldg(tab + (int64_t)k * ld + r) : -1;
 }
 
+// one warp per 128-row tile: bit k set iff some row of the tile has a neighbour at offset k
+__global__ void __launch_bounds__(256) tile_mask_kernel(const int *__restrict__ tabP, int64_t ld, int K,
+                                                        unsigned int *__restrict__ tile_mask) {
+    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= ld / 128) return;
+    unsigned int m = 0;
+    for (int k = 0; k < K; k++) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(tabP + (int64_t)k * ld + tile * 128) + lane);
+        const bool any = v.x >= 0 || v.y >= 0 || v.z >= 0 || v.w >= 0;
+        if (__any_sync(0xffffffffu, any)) m |= 1u << k;
+    }
+    if (lane == 0) tile_mask[tile] = m;
+}
+
 static size_t sort_cub_bytes(int64_t n) {
     size_t b = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, b, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, n, 32, 64);
@@ -239,8 +254,8 @@ extern "C" size_t u2_kmap_sort_scratch_bytes(int64_t n_rows) {
 }
 
 extern "C" int u2_kmap_sort_rows(const int32_t *table, int64_t ld, int64_t n_rows, int32_t K, const int32_t *bitpos_host,
-                                 const int32_t *perm_in, int32_t *perm_out, int32_t *tableP, void *scratch,
-                                 size_t scratch_bytes, u2_stream_t stream) {
+                                 const int32_t *perm_in, int32_t *perm_out, int32_t *tableP, uint32_t *tile_mask,
+                                 void *scratch, size_t scratch_bytes, u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(K > 0 && K <= 32, "u2_kmap_sort_rows: K=%d (needs 1..32)", K);
     U2_CHECK_ARG(ld >= n_rows && n_rows < 0x7FFFFFFFLL, "u2_kmap_sort_rows: bad sizes");
@@ -267,5 +282,10 @@ extern "C" int u2_kmap_sort_rows(const int32_t *table, int64_t ld, int64_t n_row
     }
     permute_table_kernel<<<dim3(grid_ld, (unsigned)K), 256, 0, st>>>(table, ld, K, perm, tableP);
     U2_LAUNCH_OK();
+    if (tile_mask) {
+        U2_CHECK_ARG(ld % 128 == 0 && ((uintptr_t)tableP & 15) == 0, "u2_kmap_sort_rows: tile masks need ld %% 128 == 0");
+        tile_mask_kernel<<<(unsigned)u2_ceil_div(ld / 128 * 32, 256), 256, 0, st>>>(tableP, ld, K, tile_mask);
+        U2_LAUNCH_OK();
+    }
     return 0;
 }

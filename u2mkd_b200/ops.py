@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
 
 _MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
-_state = {"math": MATH_FP32, "sort_tiles": True}
+_state = {"math": MATH_FP32, "sort_tiles": True, "multi_tile": False}
 
 # instrumentation used by bench.py: number of kernels this library launched, and an optional
 # per-launch CUDA-event timer for the conv kernels (the dominant kernel of the path)
@@ -41,6 +41,11 @@ def set_math(mode: str) -> None:
 def set_sort_tiles(flag: bool) -> None:
     """Mask-sorted tile order for the tensor-core conv (on by default)."""
     _state["sort_tiles"] = bool(flag)
+
+
+def set_multi_tile(flag: bool) -> None:
+    """Multi-tile CTAs for the tensor-core fwd/dgrad conv (weights shared by up to 4 tiles)."""
+    _state["multi_tile"] = bool(flag)
 
 
 def get_math() -> str:
@@ -262,22 +267,23 @@ class KernelMap:
             n_rows = self.n_in if key else self.n_out
             ld = table.shape[1]
             tabP = torch.empty_like(table)
+            tmask = torch.empty(ld // _PAD, dtype=torch.int, device=table.device)
             other = self._sorted.get(not key)
             st = _st()
             if self.same_coords and other is not None:
                 # nbrT[k][i] == nbr[K-1-k][i] on a submanifold map: the same row order is as good
                 perm = other[1]
                 check(lib().u2_kmap_sort_rows(table.data_ptr(), ld, n_rows, self.K, None, perm.data_ptr(), None,
-                                              tabP.data_ptr(), None, 0, st))
-                _count(1)
+                                              tabP.data_ptr(), tmask.data_ptr(), None, 0, st))
+                _count(2)
             else:
                 perm = torch.empty(ld, dtype=torch.int, device=table.device)
                 sbytes = lib().u2_kmap_sort_scratch_bytes(n_rows)
                 scratch = torch.empty(sbytes, dtype=torch.uint8, device=table.device)
                 check(lib().u2_kmap_sort_rows(table.data_ptr(), ld, n_rows, self.K, self._bitpos(), None, perm.data_ptr(),
-                                              tabP.data_ptr(), scratch.data_ptr(), sbytes, st))
-                _count(7)
-            self._sorted[key] = (tabP, perm)
+                                              tabP.data_ptr(), tmask.data_ptr(), scratch.data_ptr(), sbytes, st))
+                _count(8)
+            self._sorted[key] = (tabP, perm, tmask)
         return self._sorted[key]
 
     @property
@@ -372,10 +378,11 @@ def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math,
     sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device) if sbytes else None
     if side is not None and _state["sort_tiles"] and lib().u2_conv_tc_shape_supported(c_src, c_dst, K, math):
-        tabP, perm = kmap.sorted_tables(side)
+        tabP, perm, tmask = kmap.sorted_tables(side)
         _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd_perm(
-            x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), tabP.data_ptr(), perm.data_ptr(), ld, n_dst, K,
-            c_dst, y.data_ptr(), math, _ptr(scratch), sbytes, _st())))
+            x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), tabP.data_ptr(), perm.data_ptr(),
+            tmask.data_ptr() if _state["multi_tile"] else None, ld, n_dst, K, c_dst, y.data_ptr(), math, _ptr(scratch),
+            sbytes, _st())))
         return y
     _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd(
         x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
