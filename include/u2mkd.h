@@ -34,7 +34,9 @@ typedef void *u2_stream_t; /* cudaStream_t */
 enum {
     U2_MATH_FP32 = 0, /* FFMA, fp32-exact parity mode (rel 1e-4 bar)             */
     U2_MATH_TF32 = 1, /* tcgen05 kind::tf32, fp32 storage (rel 2e-2 bar)          */
-    U2_MATH_BF16 = 2  /* tcgen05 kind::f16 on bf16-rounded operands (rel 2e-2 bar) */
+    U2_MATH_BF16 = 2  /* tcgen05 kind::f16 on bf16 operands, fp32 accumulate (rel 2e-2 bar): the feature /
+                         gradient pointers of the conv entry points then address bf16 rows made by
+                         u2_cast_bf16; weights, outputs and weight gradients stay fp32             */
 };
 
 const char *u2_last_error(void);
@@ -185,6 +187,9 @@ int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int32_t C, cons
 int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
                     const float *gamma, const float *beta, const double *dsum, const double *count_dev, int32_t relu,
                     float *dx, u2_stream_t stream);
+
+/* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
+int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ from torch.profiler import profile, ProfilerActivity
 from u2mkd_b200 import models, ops, scans
 import u2mkd_b200.torchsparse as ts
 
-math = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+math = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 ops.set_math(math)
 torch.backends.cuda.matmul.allow_tf32 = math != "fp32"
 w = scans.WORKLOADS["nusc5_cr2.0_b2"]

@@ -126,3 +126,79 @@ def test_sorted_tiles_do_not_change_results(tc, oracle):
     tc.set_sort_tiles(True)
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("n,cin,cout,ks,stride", [
+    (6000, 64, 64, 3, 1), (3000, 96, 64, 3, 1), (2000, 128, 256, 3, 1), (4000, 64, 128, 2, 2), (1500, 512, 512, 3, 1),
+    (3000, 192, 384, 3, 1), (129, 64, 64, 3, 1), (2500, 32, 32, 3, 1), (700, 768, 512, 3, 1)])
+def test_conv3d_bf16_fwd_bwd(tc, oracle, n, cin, cout, ks, stride):
+    """bf16 operand mode (fp32 accumulate) against the fp32 oracle: north_star's rel 2e-2 bar."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin + cout)
+    c = rand_coords(rng, n)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32))
+    conv_o = oracle.Conv3d(cin, cout, ks, stride)
+    conv_g = gts.nn.Conv3d(cin, cout, ks, stride)
+    conv_g.load_state_dict(conv_o.state_dict())
+    conv_g.cuda()
+    fo = f.clone().requires_grad_(True)
+    yo = conv_o(oracle.SparseTensor(fo, c))
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    tc.set_math("bf16")
+    fg = f.clone().cuda().requires_grad_(True)
+    yg = conv_g(gts.SparseTensor(fg, c.cuda()))
+    yg.F.backward(g.cuda())
+    tc.set_math("fp32")
+    assert rel_err(yg.F, yo.F) < TF32_REL
+    assert rel_err(fg.grad, fo.grad) < TF32_REL
+    assert rel_err(conv_g.kernel.grad, conv_o.kernel.grad) < TF32_REL
+
+
+def test_transposed_conv_bf16(tc, oracle):
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(12)
+    c = rand_coords(rng, 6000)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], 64)).astype(np.float32))
+    down_o, up_o = oracle.Conv3d(64, 96, 2, 2), oracle.Conv3d(96, 32, 2, 2, transposed=True)
+    down_g, up_g = gts.nn.Conv3d(64, 96, 2, 2), gts.nn.Conv3d(96, 32, 2, 2, transposed=True)
+    down_g.load_state_dict(down_o.state_dict())
+    up_g.load_state_dict(up_o.state_dict())
+    down_g.cuda(), up_g.cuda()
+    tc.set_math("bf16")
+    fo = f.clone().requires_grad_(True)
+    fg = f.clone().cuda().requires_grad_(True)
+    xo, xg = oracle.SparseTensor(fo, c), gts.SparseTensor(fg, c.cuda())
+    xo.cmaps[xo.s] = xo.C
+    xg.cmaps[xg.s] = xg.C
+    yo, yg = up_o(down_o(xo)), up_g(down_g(xg))
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    yg.F.backward(g.cuda())
+    tc.set_math("fp32")
+    assert rel_err(yg.F, yo.F) < TF32_REL
+    assert rel_err(fg.grad, fo.grad) < TF32_REL
+    assert rel_err(up_g.kernel.grad, up_o.kernel.grad) < TF32_REL
+    assert rel_err(down_g.kernel.grad, down_o.kernel.grad) < TF32_REL
+
+
+def test_spvcnn_bf16_vs_oracle(tc, oracle):
+    """Whole model with bf16 conv operands: logits within the bf16 bar of the fp32 CPU oracle."""
+    from u2mkd_b200 import models, scans
+    import u2mkd_b200.torchsparse as gts
+    coords, feats = scans.make_batch([3], "nusc", 1, 0.1)
+    torch.manual_seed(0)
+    net_o = models.build_family(oracle.as_torchsparse_modules()["torchsparse"]).SPVCNN(cr=1.0, pres=0.1, vres=0.1)
+    net_g = models.product().SPVCNN(cr=1.0, pres=0.1, vres=0.1)
+    net_g.load_state_dict(net_o.state_dict())
+    net_g.cuda()
+    net_o.dropout = net_g.dropout = torch.nn.Identity()
+    tc.set_math("bf16")
+    out_g = net_g({"lidar": gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())})["x_vox"]
+    out_g.square().mean().backward()
+    tc.set_math("fp32")
+    out_o = net_o({"lidar": oracle.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords))})["x_vox"]
+    out_o.square().mean().backward()
+    assert rel_err(out_g, out_o) < TF32_REL
+    # sanity bound only: the stem gradient has crossed 48 bf16 layers backwards (max-norm, worst element)
+    assert rel_err(net_g.stem[3].kernel.grad, net_o.stem[3].kernel.grad) < 0.6

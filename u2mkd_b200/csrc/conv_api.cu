@@ -11,9 +11,10 @@ int u2_conv_wgrad_simt(const float *X, int64_t n_src, int32_t Cs, const float *d
 #ifdef U2_WITH_TC
 size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math);
 int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
-int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
+int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
                    void *scratch, size_t scratch_bytes, cudaStream_t st);
+int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
 int u2_conv_fwd_mt(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
                    const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
                    void *scratch, size_t scratch_bytes, cudaStream_t st);
@@ -21,8 +22,9 @@ int u2_conv_fwd_tma_supported(int32_t Cs, int32_t Cd, int32_t K);
 int u2_conv_fwd_tma(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
                     const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
                     void *scratch, size_t scratch_bytes, cudaStream_t st);
-int u2_conv_wgrad_tc(const float *X, int32_t Cs, const float *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
-                     int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, cudaStream_t st);
+int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
+                     int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
+                     cudaStream_t st);
 #endif
 
 extern "C" int u2_has_tensor_core_path(void) {
@@ -56,8 +58,9 @@ extern "C" int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const floa
     cudaStream_t st = (cudaStream_t)stream;
     if (math == U2_MATH_FP32) return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #ifdef U2_WITH_TC
-    if (math == U2_MATH_TF32 && u2_conv_tc_supported(Cs, Cd, K, math))
+    if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math))
         return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, nullptr, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, st);
+    U2_CHECK_ARG(math != U2_MATH_BF16, "u2_conv_fwd: shape Cs=%d Cd=%d K=%d has no bf16 kernel (caller must use TF32/FP32)", Cs, Cd, K);
     if (math == U2_MATH_TF32)  // shapes the MMA tiles cannot hold (e.g. the Cs = 4 stem conv)
         return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #endif
@@ -83,7 +86,9 @@ extern "C" int u2_conv_wgrad(const float *X, int64_t n_src, int32_t Cs, const fl
 
 extern "C" int u2_conv_wgrad_pairs_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math) {
 #ifdef U2_WITH_TC
-    return math == U2_MATH_TF32 && u2_conv_tc_supported(32, Cd, K, math) && Cs % 4 == 0;
+    if (math == U2_MATH_TF32) return u2_conv_tc_supported(32, Cd, K, math) && Cs % 4 == 0;
+    if (math == U2_MATH_BF16) return u2_conv_tc_supported(64, Cd, K, math) && Cs % 8 == 0;
+    return 0;
 #else
     (void)Cs; (void)Cd; (void)K; (void)math;
     return 0;
@@ -96,7 +101,7 @@ extern "C" int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb
 #ifdef U2_WITH_TC
     U2_CHECK_ARG(Xa && dYb && nbr && flat && nbsizes && dW, "u2_conv_wgrad_pairs: null pointer");
     U2_CHECK_ARG(u2_conv_wgrad_pairs_supported(Cs, Cd, K, math), "u2_conv_wgrad_pairs: unsupported shape/math");
-    return u2_conv_wgrad_tc(Xa, Cs, dYb, Cd, nbr, ld, n_rows, K, flat, nbsizes, swap, dW, (cudaStream_t)stream);
+    return u2_conv_wgrad_tc(Xa, Cs, dYb, Cd, nbr, ld, n_rows, K, flat, nbsizes, swap, dW, math, (cudaStream_t)stream);
 #else
     u2_set_error("u2_conv_wgrad_pairs: built without the tcgen05 path");
     return 1;
@@ -110,7 +115,11 @@ extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const
 #ifdef U2_WITH_TC
     if (check_common(X, W, tableP, Y, Cs, Cd, K, ld, n_dst, "u2_conv_fwd_perm")) return 1;
     U2_CHECK_ARG(perm != nullptr, "u2_conv_fwd_perm: null perm");
-    U2_CHECK_ARG(math == U2_MATH_TF32 && u2_conv_tc_supported(Cs, Cd, K, math), "u2_conv_fwd_perm: unsupported shape/math");
+    U2_CHECK_ARG((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math),
+                 "u2_conv_fwd_perm: unsupported shape/math");
+    if (math == U2_MATH_BF16)
+        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
+                              (cudaStream_t)stream);
     static const int use_tma = getenv("U2_NO_TMA_GATHER") ? 0 : 1;
     if (tile_mask && use_tma && u2_conv_fwd_tma_supported(Cs, Cd, K))
         return u2_conv_fwd_tma(X, n_src, Cs, W, w_transposed, tableP, perm, tile_mask, ld, n_dst, K, Cd, Y, scratch,
@@ -132,5 +141,15 @@ extern "C" int u2_conv_tc_shape_supported(int32_t Cs, int32_t Cd, int32_t K, int
 #else
     (void)Cs; (void)Cd; (void)K; (void)math;
     return 0;
+#endif
+}
+
+extern "C" int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    return u2_cast_bf16_impl(x, n, y, (cudaStream_t)stream);
+#else
+    (void)x; (void)n; (void)y; (void)stream;
+    u2_set_error("u2_cast_bf16: built without the tcgen05 path");
+    return 1;
 #endif
 }

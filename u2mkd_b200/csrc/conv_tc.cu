@@ -91,6 +91,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (BF16) umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -122,12 +136,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// BF16 x BF16 -> F32 (kind::f16), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 constexpr int A_ROW_GROUP = TILE_M * 16;      // 2048: bytes of one 16-byte K chunk over 128 rows
 constexpr int A_LBO = A_ROW_GROUP + 16;       // +16: bank-conflict-free 16-byte gather writes
 
 struct FwdParams {
-    const float *X;
-    const float *Wt;   // pre-tiled weights
+    const uint8_t *X;   // fp32 (tf32 math) or bf16 rows, Cs channels each
+    const uint8_t *Wt;  // pre-tiled weights, same element type
     const int *table;  // [K, ld] source row per (offset, tile row), -1 = none
     const int *perm;   // tile row -> destination row (mask-sorted tiles), or nullptr = identity
     float *Y;
@@ -136,9 +155,11 @@ struct FwdParams {
     long long *dbg;  // optional per-CTA phase timestamps (U2_DEBUG_CONV_TIMING)
 };
 
-template <int KC>
+// ROWB = bytes of one gathered row per pipeline stage (128 or 64): 32/16 fp32 or 64/32 bf16 channels.
+template <int ROWB, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParams p) {
-    constexpr int CHUNKS = KC / 4;            // 16-byte chunks per row per stage
+    constexpr int ES = BF16 ? 2 : 4;          // element size
+    constexpr int CHUNKS = ROWB / 16;         // 16-byte chunks per row per stage
     constexpr int ROWS_PER_IT = TILE_M / CHUNKS;  // rows covered by one cp.async round of the 128 producers
     constexpr int A_BYTES = CHUNKS * A_LBO;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     const int nt = blockIdx.y;
     long long *dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
-    const int n_cc = p.Cs / KC;
+    const int n_cc = p.Cs * ES / ROWB;
     const int n_nt = p.Cd / NT;
 
     if (tid == 0) {
@@ -224,10 +245,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
 #pragma unroll
             for (int i = 0; i < CHUNKS; i++) {
                 const int src = tab_k[i * ROWS_PER_IT];
-                off[i] = src >= 0 ? (uint32_t)src * (uint32_t)p.Cs + (uint32_t)(chunk * 4) : 0xFFFFFFFFu;
+                off[i] = src >= 0 ? (uint32_t)src * (uint32_t)(p.Cs * ES) + (uint32_t)(chunk * 16) : 0xFFFFFFFFu;  // bytes
             }
-            const float *xc = p.X;
-            for (int cc = 0; cc < n_cc; cc++, xc += KC) {
+            const uint8_t *xc = p.X;
+            for (int cc = 0; cc < n_cc; cc++, xc += ROWB) {
                 mbar_wait(s_empty + s, ph ^ 1u);
                 const uint32_t a_dst = smem_u32(s_stage + (size_t)s * stage_bytes) + dst0;
 #pragma unroll
@@ -293,7 +314,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                 for (int cc = 0; cc < n_cc; cc++) {
                     mbar_wait(s_empty + s, ph ^ 1u);
                     const uint32_t b_base = smem_u32(s_stage + (size_t)s * stage_bytes + A_BYTES);
-                    const float *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(KC * NT);
+                    const uint8_t *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(ROWB * NT);
                     mbar_arrive_expect_tx(s_full + s, (uint32_t)B_BYTES);
                     bulk_g2s(b_base, blob, (uint32_t)B_BYTES, s_full + s);
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         }
     } else {
         // ============================ MMA issuer ============================
-        const uint32_t idesc = make_idesc_tf32(TILE_M, NT);
+        const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, NT) : make_idesc_tf32(TILE_M, NT);
         int s = 0;
         uint32_t ph = 0;
         for (int it = 0; it < n_items; it++) {
@@ -313,10 +334,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                 const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
                 const uint32_t b_base = a_base + A_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < KC / 8; kk++) {
+                for (int kk = 0; kk < ROWB / 32; kk++) {  // one MMA consumes 32 bytes of K: 8 tf32 or 16 bf16
                     const uint64_t ad = make_smem_desc(a_base + kk * 2 * A_LBO, A_LBO, 128);
                     const uint64_t bd = make_smem_desc(b_base + kk * 2 * B_LBO, B_LBO, 128);
-                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    umma<BF16>(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(s_empty + s);
                 if (it == n_items - 1) umma_commit(s_accum);
@@ -826,36 +847,51 @@ __global__ void __launch_bounds__(256) pretile_weights_kernel(const float *__res
 // cycle and no gathered byte is spent on missing neighbours.  Partial tiles are combined with
 // 16-byte fp32 reductions into dW (zeroed by the caller).
 constexpr int WG_PAIRS = 4096;  // pairs per CTA
-constexpr int WG_KR = 32;       // pairs per pipeline stage (4 MMAs of K=8)
-constexpr int WG_ATOM = WG_KR * 128;  // 4096 bytes: 32 pairs x 32 channels
 
-__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
-    return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+__host__ __device__ constexpr uint32_t make_idesc_mn(bool bf16, int M, int N) {
+    return (bf16 ? make_idesc_bf16(M, N) : make_idesc_tf32(M, N)) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
 }
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);  // SWIZZLE_128B_BASE32B
-}
-// physical 16-byte chunk of logical chunk c (0..7) in pair row r of a SW128_32B atom
-__device__ __forceinline__ int swz_chunk(int c, int r) { return ((((c >> 1) ^ (r & 3)) << 1) | (c & 1)); }
+
+// Geometry of one pipeline stage of the wgrad kernel.
+//   tf32: SWIZZLE_128B_BASE32B, atoms of 32 channels x 4 pairs, MMA K = 8 pairs, 32 pairs / stage
+//   bf16: SWIZZLE_128B,         atoms of 64 channels x 8 pairs, MMA K = 16 pairs, 64 pairs / stage
+template <bool BF16>
+struct WgGeom {
+    static constexpr int ES = BF16 ? 2 : 4;
+    static constexpr int KR = BF16 ? 64 : 32;          // pairs per stage (4 MMAs)
+    static constexpr int CPA = 128 / ES;               // channels per 128-byte atom row
+    static constexpr int ATOM = KR * 128;              // bytes: KR pair-rows x 128 B  (= LBO between channel atoms)
+    static constexpr int A_ATOMS = TILE_M / CPA;       // 4 / 2
+    static constexpr int A_BYTES = A_ATOMS * ATOM;     // 16 KB
+    static constexpr int SBO = BF16 ? 1024 : 512;      // bytes between swizzle atoms along the pair axis
+    static constexpr int MMA_ADV = BF16 ? 2048 : 1024; // bytes of pair rows one MMA consumes
+    static constexpr int RB = KR / 32;                 // 32-row blocks per stage
+    static constexpr uint64_t LAYOUT = BF16 ? 2 : 1;   // SWIZZLE_128B / SWIZZLE_128B_BASE32B
+    // physical 16-byte chunk of logical chunk c (0..7) in pair row r
+    __device__ static __forceinline__ int swz(int c, int r) {
+        return BF16 ? (c ^ (r & 7)) : ((((c >> 1) ^ (r & 3)) << 1) | (c & 1));
+    }
+};
 
 struct WgradParams {
-    const float *X;    // rows indexed by the "a" side of a pair
-    const float *dY;   // rows indexed by the "b" side
-    const int *nbr;    // [K, ld] neighbour table the pair list was compacted from
-    const int *flat;   // compacted flat indices k*ld + out_row of the valid entries
+    const uint8_t *X;   // rows indexed by the "a" side of a pair (fp32 or bf16)
+    const uint8_t *dY;  // rows indexed by the "b" side
+    const int *nbr;     // [K, ld] neighbour table the pair list was compacted from
+    const int *flat;    // compacted flat indices k*ld + out_row of the valid entries
     const int *nbsizes;
     float *dW;
     int64_t ld;
     int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt;
 };
 
+template <bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradParams p) {
+    using G = WgGeom<BF16>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int NT = p.NT;
-    const int n_batoms = (NT + 31) / 32;
-    constexpr int A_BYTES = 4 * WG_ATOM;  // 16 KB
-    const int B_BYTES = n_batoms * WG_ATOM;
-    const int stage_bytes = A_BYTES + B_BYTES;
+    const int n_batoms = (NT + G::CPA - 1) / G::CPA;
+    const int B_BYTES = n_batoms * G::ATOM;
+    const int stage_bytes = G::A_BYTES + B_BYTES;
     int2 *s_pairs = reinterpret_cast<int2 *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *s_full = reinterpret_cast<uint64_t *>(s_pairs + WG_PAIRS);
     uint64_t *s_empty = s_full + MAX_STAGES;
@@ -872,7 +908,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     const int c0 = blockIdx.x * WG_PAIRS;
     if (c0 >= n_k) return;
     const int n_pairs = min(WG_PAIRS, n_k - c0);
-    const int n_items = (n_pairs + WG_KR - 1) / WG_KR;
+    const int n_items = (n_pairs + G::KR - 1) / G::KR;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -889,7 +925,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     // (a-row, b-row) of every pair of the chunk; padded to a whole stage with -1
     {
         const int *flat = p.flat + koff + c0;
-        const int padded = n_items * WG_KR;
+        const int padded = n_items * G::KR;
         for (int pr = tid; pr < padded; pr += NUM_THREADS) {
             int2 ab = make_int2(-1, -1);
             if (pr < n_pairs) {
@@ -909,37 +945,40 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
 
     if (warp < 4) {
         // ============================ producers: gather both operands ============================
-        const int cc = lane & 7;     // 16-byte chunk inside a 32-channel atom
+        const int cc = lane & 7;     // 16-byte chunk inside a 128-byte atom row
         const int rsub = lane >> 3;  // pair inside a group of 4
-        const int a_ch = m0 + (warp * 8 + cc) * 4;
+        // A: warp w owns unit w = (channel atom, 32-row block)
+        const int a_atom = warp / G::RB, a_rb = warp % G::RB;
+        const int a_ch = m0 + a_atom * G::CPA + cc * (16 / G::ES);
         const bool a_ch_ok = a_ch < p.Cs;
+        const size_t a_pitch = (size_t)p.Cs * G::ES, b_pitch = (size_t)p.Cd * G::ES;
         for (int it = 0; it < n_items; it++) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(s_empty + s, ph ^ 1u);
             const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t b_base = a_base + A_BYTES;
-            const int2 *pairs = s_pairs + it * WG_KR;
-            // A: warp w owns channel atom w; 8 instructions x (4 pairs x 128 B)
+            const uint32_t b_base = a_base + G::A_BYTES;
+            const int2 *pairs = s_pairs + it * G::KR;
 #pragma unroll
-            for (int i = 0; i < WG_KR / 4; i++) {
-                const int r = 4 * i + rsub;
+            for (int i = 0; i < 8; i++) {
+                const int r = a_rb * 32 + 4 * i + rsub;
                 const int arow = pairs[r].x;
                 const bool ok = arow >= 0 && a_ch_ok;
-                const float *src = p.X + (int64_t)(ok ? arow : 0) * p.Cs + (ok ? a_ch : 0);
-                cp_async16(a_base + warp * WG_ATOM + r * 128 + swz_chunk(cc, r) * 16, src, ok ? 16u : 0u);
+                const uint8_t *src = p.X + (ok ? (size_t)arow * a_pitch + (size_t)a_ch * G::ES : 0);
+                cp_async16(a_base + a_atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u);
             }
-            // B: warp w owns channel atoms w, w+4, ...
-            for (int atom = warp; atom < n_batoms; atom += 4) {
-                const int ch = (atom * 8 + cc) * 4;
+            // B: units (channel atom, 32-row block) w, w+4, ...
+            for (int u = warp; u < n_batoms * G::RB; u += 4) {
+                const int atom = u / G::RB, rb = u % G::RB;
+                const int ch = atom * G::CPA + cc * (16 / G::ES);
                 const bool ch_ok = ch < NT;
 #pragma unroll
-                for (int i = 0; i < WG_KR / 4; i++) {
-                    const int r = 4 * i + rsub;
+                for (int i = 0; i < 8; i++) {
+                    const int r = rb * 32 + 4 * i + rsub;
                     const int brow = pairs[r].y;
                     const bool ok = brow >= 0 && ch_ok;
-                    const float *src = p.dY + (int64_t)(ok ? brow : 0) * p.Cd + n0 + (ok ? ch : 0);
-                    cp_async16(b_base + atom * WG_ATOM + r * 128 + swz_chunk(cc, r) * 16, src, ok ? 16u : 0u);
+                    const uint8_t *src = p.dY + (ok ? (size_t)brow * b_pitch + (size_t)(n0 + ch) * G::ES : 0);
+                    cp_async16(b_base + atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u);
                 }
             }
             cp_async_mbar_arrive_noinc(s_full + s);
@@ -963,7 +1002,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
         }
     } else if (warp == 5) {
         // ============================ MMA issuer ============================
-        const uint32_t idesc = make_idesc_tf32_mn(TILE_M, NT);
+        const uint32_t idesc = make_idesc_mn(BF16, TILE_M, NT);
         for (int it = 0; it < n_items; it++) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -972,12 +1011,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
             proxy_fence_async();
             if (lane == 0) {
                 const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_base = a_base + A_BYTES;
+                const uint32_t b_base = a_base + G::A_BYTES;
 #pragma unroll
-                for (int g = 0; g < WG_KR / 8; g++) {
-                    const uint64_t ad = make_smem_desc_sw128_32b(a_base + g * 1024, WG_ATOM, 512);
-                    const uint64_t bd = make_smem_desc_sw128_32b(b_base + g * 1024, WG_ATOM, 512);
-                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                for (int g = 0; g < 4; g++) {
+                    const uint64_t ad = make_smem_desc(a_base + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
+                    const uint64_t bd = make_smem_desc(b_base + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
+                    umma<BF16>(tmem_base, ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
                 }
                 umma_commit(s_empty + s);
                 if (it == n_items - 1) umma_commit(s_accum);
@@ -990,6 +1029,41 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+__device__ __forceinline__ unsigned int pack_bf16x2(float lo, float hi) {
+    unsigned int r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// fp32 weights -> bf16 blobs [k][cc][nt][chunk][n][8] (K-major UMMA layout, 16-byte chunk = 8 channels)
+template <bool WT>
+__global__ void __launch_bounds__(256) pretile_weights_bf16_kernel(const float *__restrict__ W, uint4 *__restrict__ out, int K,
+                                                                   int Cs, int Cd, int KC, int NT) {
+    const int64_t total = (int64_t)K * Cs * Cd / 8;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int chunks = KC / 8, n_cc = Cs / KC, n_nt = Cd / NT;
+    int64_t r = t;
+    const int n = (int)(r % NT); r /= NT;
+    const int chunk = (int)(r % chunks); r /= chunks;
+    const int nti = (int)(r % n_nt); r /= n_nt;
+    const int cc = (int)(r % n_cc); r /= n_cc;
+    const int k = (int)r;
+    const int cs = cc * KC + chunk * 8, cd = nti * NT + n;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+        v[e] = WT ? __ldg(W + ((int64_t)k * Cd + cd) * Cs + cs + e) : __ldg(W + ((int64_t)k * Cs + cs + e) * Cd + cd);
+    out[t] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4 *__restrict__ x, int64_t n8, uint4 *__restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+    y[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
 int pick_nt(int Cd) {
     const int tiles = (Cd + 255) / 256;
     if (Cd % tiles) return 0;
@@ -997,49 +1071,70 @@ int pick_nt(int Cd) {
     return (nt % 16 == 0 && nt >= 16) ? nt : 0;
 }
 
-int pick_kc(int Cs) { return Cs % 32 == 0 ? 32 : (Cs % 16 == 0 ? 16 : 0); }
+// bytes of a gathered row per stage (128 preferred, 64 otherwise); 0 = shape not supported
+int pick_rowb(int Cs, int es) { return (Cs * es) % 128 == 0 ? 128 : ((Cs * es) % 64 == 0 ? 64 : 0); }
+int pick_kc(int Cs) { return pick_rowb(Cs, 4) / 4; }
 
 }  // namespace
 
 int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math) {
-    return math == U2_MATH_TF32 && pick_kc(Cs) && pick_nt(Cd) && K <= 32;
+    if (math == U2_MATH_TF32) return pick_rowb(Cs, 4) && pick_nt(Cd) && K <= 32;
+    if (math == U2_MATH_BF16) return pick_rowb(Cs, 2) && pick_nt(Cd) && K <= 32 && Cs % 8 == 0;
+    return 0;
 }
 
 size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd, int32_t math) {
     (void)n_dst;
     if (!u2_conv_tc_supported(Cs, Cd, K, math)) return 0;
-    return (size_t)K * Cs * Cd * sizeof(float);
+    return (size_t)K * Cs * Cd * (math == U2_MATH_BF16 ? 2 : 4);
 }
 
-int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
+template <int ROWB, bool BF16>
+static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_t st) {
+    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_fwd_tc_kernel<ROWB, BF16><<<grid, NUM_THREADS, smem, st>>>(p);
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+// X: fp32 rows (math TF32) or bf16 rows (math BF16); W always the fp32 parameter tensor.
+int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
                    void *scratch, size_t scratch_bytes, cudaStream_t st) {
-    (void)math;
-    U2_CHECK_ARG(n_src * (int64_t)Cs < 0xFFFFFFFFLL, "u2_conv_fwd_tc: source tensor too large for 32-bit element offsets");
+    const bool bf16 = math == U2_MATH_BF16;
+    const int es = bf16 ? 2 : 4;
+    U2_CHECK_ARG(n_src * (int64_t)Cs * es < 0xFFFFFFFFLL, "u2_conv_fwd_tc: source tensor too large for 32-bit byte offsets");
     if (n_dst == 0) return 0;
-    const int KC = pick_kc(Cs), NT = pick_nt(Cd);
-    U2_CHECK_ARG(KC && NT && K <= 32, "u2_conv_fwd_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
+    const int ROWB = pick_rowb(Cs, es), NT = pick_nt(Cd);
+    const int KC = ROWB / es;
+    U2_CHECK_ARG(ROWB && NT && K <= 32, "u2_conv_fwd_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
     U2_CHECK_ARG(ld % TILE_M == 0, "u2_conv_fwd_tc: table leading dimension must be a multiple of 128");
-    U2_CHECK_ARG(scratch && scratch_bytes >= (size_t)K * Cs * Cd * sizeof(float), "u2_conv_fwd_tc: scratch too small");
+    U2_CHECK_ARG(scratch && scratch_bytes >= (size_t)K * Cs * Cd * es, "u2_conv_fwd_tc: scratch too small");
     U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)scratch) & 15) == 0,
                  "u2_conv_fwd_tc: pointers must be 16-byte aligned");
-    const int64_t total4 = (int64_t)K * Cs * Cd / 4;
-    if (w_transposed)
-        pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-    else
-        pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
+    if (bf16) {
+        const int64_t total8 = (int64_t)K * Cs * Cd / 8;
+        if (w_transposed)
+            pretile_weights_bf16_kernel<true><<<(unsigned)u2_ceil_div(total8, 256), 256, 0, st>>>(W, (uint4 *)scratch, K, Cs, Cd, KC, NT);
+        else
+            pretile_weights_bf16_kernel<false><<<(unsigned)u2_ceil_div(total8, 256), 256, 0, st>>>(W, (uint4 *)scratch, K, Cs, Cd, KC, NT);
+    } else {
+        const int64_t total4 = (int64_t)K * Cs * Cd / 4;
+        if (w_transposed)
+            pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
+        else
+            pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
+    }
     U2_LAUNCH_OK();
 
     FwdParams p;
-    p.X = X; p.Wt = (const float *)scratch; p.table = table; p.perm = perm; p.Y = Y;
-    static long long *g_dbg = nullptr;
-    if (getenv("U2_DEBUG_CONV_TIMING") && !g_dbg) cudaMalloc(&g_dbg, (size_t)8 * 8 * 65536);
-    p.dbg = g_dbg;
+    p.X = (const uint8_t *)X; p.Wt = (const uint8_t *)scratch; p.table = table; p.perm = perm; p.Y = Y;
+    p.dbg = nullptr;
     p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
     int cols = 32;
     while (cols < NT) cols <<= 1;
     p.tmem_cols = cols;
-    const int chunks = KC / 4;
+    const int chunks = ROWB / 16;
     const size_t stage_bytes = (size_t)chunks * A_LBO + (size_t)chunks * NT * 16;
     const size_t fixed = (size_t)K * TILE_M * sizeof(int) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
     // prefer two CTAs per SM (one gathers while the other drains its accumulator) if that
@@ -1053,50 +1148,39 @@ int u2_conv_fwd_tc(const float *X, int64_t n_src, int32_t Cs, const float *W, in
     const size_t smem = stages * stage_bytes + fixed;
     // with a row permutation the tiles run over the (padded) table rows, destination rows come from perm
     dim3 grid((unsigned)u2_ceil_div(perm ? ld : n_dst, TILE_M), (unsigned)(Cd / NT));
-    if (KC == 32) {
-        U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(p);
-    } else {
-        U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_tc_kernel<16><<<grid, NUM_THREADS, smem, st>>>(p);
-    }
+    if (bf16) return ROWB == 128 ? launch_fwd_v1<128, true>(p, grid, smem, st) : launch_fwd_v1<64, true>(p, grid, smem, st);
+    return ROWB == 128 ? launch_fwd_v1<128, false>(p, grid, smem, st) : launch_fwd_v1<64, false>(p, grid, smem, st);
+}
+
+int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st) {
+    U2_CHECK_ARG(n % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0, "u2_cast_bf16: n %% 8 == 0 and 16-byte alignment required");
+    if (n == 0) return 0;
+    cast_bf16_kernel<<<(unsigned)u2_ceil_div(n / 8, 256), 256, 0, st>>>((const float4 *)x, n / 8, (uint4 *)y);
     U2_LAUNCH_OK();
-    if (g_dbg) {
-        const int nb = (int)(grid.x * grid.y) < 65536 ? (int)(grid.x * grid.y) : 65536;
-        long long *h = (long long *)malloc((size_t)nb * 64);
-        cudaMemcpy(h, g_dbg, (size_t)nb * 64, cudaMemcpyDeviceToHost);
-        double pro = 0, prod = 0, mma_tail = 0, epi = 0, tot = 0, items = 0;
-        long long tmin = h[0], tmax = 0;
-        for (int b = 0; b < nb; b++) {
-            long long *d = h + b * 8;
-            pro += d[1] - d[0]; prod += d[2] - d[1]; mma_tail += d[3] - d[2]; epi += d[4] - d[3]; tot += d[5] - d[0]; items += d[6];
-            if (d[0] < tmin) tmin = d[0];
-            if (d[5] > tmax) tmax = d[5];
-        }
-        printf("[conv timing] Cs=%d Cd=%d NT=%d stages=%d ctas=%d smem=%zu | avg cycles/CTA: prologue %.0f, produce %.0f, wait-accum %.0f, epilogue %.0f, total %.0f | items/CTA %.1f -> %.0f cyc/item\n",
-               Cs, Cd, NT, stages, nb, smem, pro / nb, prod / nb, mma_tail / nb, epi / nb, tot / nb, items / nb, prod / (items > 0 ? items : 1));
-        free(h);
-    }
     return 0;
 }
 
-int u2_conv_wgrad_tc(const float *X, int32_t Cs, const float *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
-                     int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, cudaStream_t st) {
+// X / dY: fp32 rows (math TF32) or bf16 rows (math BF16)
+int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
+                     int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
+                     cudaStream_t st) {
+    const bool bf16 = math == U2_MATH_BF16;
     const int NT = pick_nt(Cd);
-    U2_CHECK_ARG(NT && Cs % 4 == 0 && K <= 32, "u2_conv_wgrad_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
+    U2_CHECK_ARG(NT && Cs % (bf16 ? 8 : 4) == 0 && K <= 32, "u2_conv_wgrad_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
     U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)dY | (uintptr_t)dW) & 15) == 0, "u2_conv_wgrad_tc: pointers must be 16-byte aligned");
     U2_CHECK_ARG((int64_t)K * ld < 0x7FFFFFFFLL, "u2_conv_wgrad_tc: table too large for int32 flat indices");
     U2_CUDA_OK(cudaMemsetAsync(dW, 0, (size_t)K * Cs * Cd * sizeof(float), st));
     if (n_rows == 0) return 0;
     WgradParams p;
-    p.X = X; p.dY = dY; p.nbr = nbr; p.flat = flat; p.nbsizes = nbsizes; p.dW = dW;
+    p.X = (const uint8_t *)X; p.dY = (const uint8_t *)dY; p.nbr = nbr; p.flat = flat; p.nbsizes = nbsizes; p.dW = dW;
     p.ld = ld; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT; p.swap = swap;
     p.n_mt = (Cs + TILE_M - 1) / TILE_M;
     p.n_nt = Cd / NT;
     int cols = 32;
     while (cols < NT) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t stage_bytes = (size_t)(4 + (NT + 31) / 32) * WG_ATOM;
+    const int cpa = bf16 ? 64 : 32, atom = bf16 ? 8192 : 4096;
+    const size_t stage_bytes = (size_t)(TILE_M / cpa + (NT + cpa - 1) / cpa) * atom;
     const size_t fixed = (size_t)WG_PAIRS * sizeof(int2) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
     const size_t budget = 227 * 1024;
     int stages = (int)((budget / 2 - fixed - 1024) / stage_bytes);
@@ -1107,8 +1191,13 @@ int u2_conv_wgrad_tc(const float *X, int32_t Cs, const float *dY, int32_t Cd, co
     const size_t smem = stages * stage_bytes + fixed;
     // a single offset has at most n_rows pairs (one per row of the table's row side)
     dim3 grid((unsigned)u2_ceil_div(n_rows, WG_PAIRS), (unsigned)K, (unsigned)(p.n_mt * p.n_nt));
-    U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_wgrad_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(p);
+    if (bf16) {
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
+    } else {
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(p);
+    }
     U2_LAUNCH_OK();
     return 0;
 }

@@ -375,6 +375,7 @@ def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math,
     K, ld = table.shape
     n_src, c_src = x.shape
     y = torch.empty((n_dst, c_dst), dtype=torch.float32, device=x.device)
+    assert (x.dtype == torch.bfloat16) == (math == MATH_BF16), (x.dtype, math)
     sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device) if sbytes else None
     if side is not None and _state["sort_tiles"] and lib().u2_conv_tc_shape_supported(c_src, c_dst, K, math):
@@ -388,6 +389,23 @@ def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math,
         x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
         math, _ptr(scratch), sbytes, _st())))
     return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy of a feature matrix (operand conversion of the bf16 conv mode)."""
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().u2_cast_bf16(x.data_ptr(), x.numel(), y.data_ptr(), _st()))
+    _count()
+    return y
+
+
+def _layer_math(math: int, c_src: int, c_dst: int, K: int) -> int:
+    """bf16 kernels exist for channel counts that fill their tiles; other layers of a bf16 run use
+    the tf32 entry points (which themselves fall back to FFMA for e.g. the Cin=4 stem conv)."""
+    if math == MATH_BF16 and not lib().u2_conv_tc_shape_supported(c_src, c_dst, K, MATH_BF16):
+        return MATH_TF32
+    return math
 
 
 class ConvolutionFn(Function):
@@ -408,37 +426,49 @@ class ConvolutionFn(Function):
         else:
             table, n_dst = kmap.nbrT, kmap.n_in
             assert feats.shape[0] == kmap.n_out, (feats.shape, kmap.sizes)
-        out = _conv_gather_gemm("fwd", kmap, feats, weight, False, table, n_dst, cout, math, side=bool(transposed))
-        ctx.save_for_backward(feats, weight)
+        m_fwd = _layer_math(math, cin, cout, K)
+        x_op = cast_bf16(feats) if m_fwd == MATH_BF16 else feats
+        out = _conv_gather_gemm("fwd", kmap, x_op, weight, False, table, n_dst, cout, m_fwd, side=bool(transposed))
+        # the bf16 copy (half the bytes) is what wgrad needs later; otherwise keep the fp32 rows
+        ctx.save_for_backward(x_op, weight)
         ctx.misc = (kmap, transposed, math, in_dtype)
         return out.to(in_dtype)
 
     @staticmethod
     def backward(ctx, grad_output):
-        feats, weight = ctx.saved_tensors
+        x_op, weight = ctx.saved_tensors
         kmap, transposed, math, in_dtype = ctx.misc
         g = grad_output.contiguous().float()
         K, cin, cout = weight.shape
         grad_feats = grad_weight = None
         fwd_table = kmap.nbrT if transposed else kmap.nbr
+        x_is_bf16 = x_op.dtype == torch.bfloat16
+        m_dgrad = _layer_math(math, cout, cin, K) if ctx.needs_input_grad[0] else MATH_FP32
+        m_wgrad = MATH_BF16 if (x_is_bf16 and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, MATH_BF16)) else \
+            (MATH_TF32 if math != MATH_FP32 else MATH_FP32)
+        g_bf16 = cast_bf16(g) if MATH_BF16 in (m_dgrad, m_wgrad) else None
         if ctx.needs_input_grad[0]:
             bwd_table = kmap.nbr if transposed else kmap.nbrT
-            grad_feats = _conv_gather_gemm("dgrad", kmap, g, weight, True, bwd_table, feats.shape[0], cin, math,
-                                           side=not transposed).to(in_dtype)
-        if ctx.needs_input_grad[1] and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, math):
+            grad_feats = _conv_gather_gemm("dgrad", kmap, g_bf16 if m_dgrad == MATH_BF16 else g, weight, True, bwd_table,
+                                           x_op.shape[0], cin, m_dgrad, side=not transposed).to(in_dtype)
+        if ctx.needs_input_grad[1]:
+            if x_is_bf16 and m_wgrad != MATH_BF16:
+                x_op = x_op.float()  # (not reached for SPVCNN shapes: bf16 fwd implies bf16 wgrad)
             grad_weight = torch.empty_like(weight)
-            flat = kmap.flat_pairs
-            _timed("wgrad", kmap, g.shape[0], K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
-                feats.data_ptr(), cin, g.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
-                flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), math, _st())))
-        elif ctx.needs_input_grad[1]:
-            grad_weight = torch.empty_like(weight)
-            n_dst = g.shape[0]
-            sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, math)
-            scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device) if sbytes else None
-            _timed("wgrad", kmap, n_dst, K, cin, cout, lambda: check(lib().u2_conv_wgrad(
-                feats.data_ptr(), feats.shape[0], cin, g.data_ptr(), n_dst, cout, fwd_table.data_ptr(),
-                fwd_table.shape[1], K, grad_weight.data_ptr(), math, _ptr(scratch), sbytes, _st())))
+            if m_wgrad != MATH_FP32 and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, m_wgrad):
+                flat = kmap.flat_pairs
+                gw = g_bf16 if m_wgrad == MATH_BF16 else g
+                _timed("wgrad", kmap, g.shape[0], K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                    x_op.data_ptr(), cin, gw.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
+                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), m_wgrad, _st())))
+            else:
+                n_dst = g.shape[0]
+                m = MATH_FP32 if m_wgrad == MATH_BF16 else m_wgrad
+                sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, m)
+                scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device) if sbytes else None
+                _timed("wgrad", kmap, n_dst, K, cin, cout, lambda: check(lib().u2_conv_wgrad(
+                    x_op.data_ptr(), x_op.shape[0], cin, g.data_ptr(), n_dst, cout, fwd_table.data_ptr(),
+                    fwd_table.shape[1], K, grad_weight.data_ptr(), m, _ptr(scratch), sbytes, _st())))
         return grad_feats, grad_weight, None, None, None
 
 
