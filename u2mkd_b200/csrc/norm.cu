@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int BN_ROWS_PER_BLOCK = 512;
+constexpr int BN_ROWS_PER_BLOCK = 128;  // small row blocks: thousands of CTAs, 4 independent 16-byte loads per thread in flight
 
 struct BnGeom {
     int tx;  // float4 columns = C / 4
@@ -26,6 +26,27 @@ inline BnGeom bn_geom(int C) {
     return g;
 }
 
+__device__ __forceinline__ void acc4(float4 &s, const float4 v) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+__device__ __forceinline__ void acc4sq(float4 &q, const float4 v) { q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w; }
+
+__device__ __forceinline__ void block_reduce_to_global(float4 s, float4 q, int tx, int ty, int cx, int ry, float4 *s_red,
+                                                       double *out) {
+    s_red[ry * tx + cx] = s;
+    s_red[(ty + ry) * tx + cx] = q;
+    __syncthreads();
+    if (ry == 0) {
+        for (int j = 1; j < ty; j++) {
+            acc4(s, s_red[j * tx + cx]);
+            acc4(q, s_red[(ty + j) * tx + cx]);
+        }
+        const int C = tx * 4, c = cx * 4;
+        atomicAdd(out + c + 0, (double)s.x); atomicAdd(out + c + 1, (double)s.y);
+        atomicAdd(out + c + 2, (double)s.z); atomicAdd(out + c + 3, (double)s.w);
+        atomicAdd(out + C + c + 0, (double)q.x); atomicAdd(out + C + c + 1, (double)q.y);
+        atomicAdd(out + C + c + 2, (double)q.z); atomicAdd(out + C + c + 3, (double)q.w);
+    }
+}
+
 // sums[c] += sum_rows x[r][c];  sums[C + c] += sum_rows x[r][c]^2
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float4 *__restrict__ x, int64_t n, int tx, int ty,
                                                        double *__restrict__ sums) {
@@ -35,28 +56,18 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float4 *__restrict_
     const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
     if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * tx * 4] = (double)n;  // local row count rides along
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ry < ty) {
-        for (int64_t r = r0 + ry; r < r1; r += ty) {
-            const float4 v = __ldg(x + r * tx + cx);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
-        }
-        s_red[ry * tx + cx] = s;
-        s_red[(ty + ry) * tx + cx] = q;
+    int64_t r = r0 + ry;
+    for (; r + 3 * ty < r1; r += 4 * ty) {
+        const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
+        const float4 v2 = __ldg(x + (r + 2 * ty) * tx + cx), v3 = __ldg(x + (r + 3 * ty) * tx + cx);
+        acc4(s, v0); acc4sq(q, v0); acc4(s, v1); acc4sq(q, v1);
+        acc4(s, v2); acc4sq(q, v2); acc4(s, v3); acc4sq(q, v3);
     }
-    __syncthreads();
-    if (ry == 0) {
-        for (int j = 1; j < ty; j++) {
-            const float4 a = s_red[j * tx + cx], b = s_red[(ty + j) * tx + cx];
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-            q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
-        }
-        const int C = tx * 4, c = cx * 4;
-        atomicAdd(sums + c + 0, (double)s.x); atomicAdd(sums + c + 1, (double)s.y);
-        atomicAdd(sums + c + 2, (double)s.z); atomicAdd(sums + c + 3, (double)s.w);
-        atomicAdd(sums + C + c + 0, (double)q.x); atomicAdd(sums + C + c + 1, (double)q.y);
-        atomicAdd(sums + C + c + 2, (double)q.z); atomicAdd(sums + C + c + 3, (double)q.w);
+    for (; r < r1; r += ty) {
+        const float4 v = __ldg(x + r * tx + cx);
+        acc4(s, v); acc4sq(q, v);
     }
+    block_reduce_to_global(s, q, tx, ty, cx, ry, s_red, sums);
 }
 
 // per-channel mean / invstd from the (possibly all-reduced) sums; sums[2C] = total row count
@@ -78,28 +89,34 @@ __global__ void bn_finalize_kernel(const double *__restrict__ sums, int C, float
     }
 }
 
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// y = x * scale + shift (+ReLU); scale = invstd * gamma, shift = beta - mean * scale: computed once per thread
 template <bool RELU>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict__ x, int64_t n4, int tx,
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict__ x, int64_t n, int tx, int ty,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
                                                        float4 *__restrict__ y) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int c = (int)(i % tx) * 4;
-    const float4 v = __ldg(x + i);
-    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean + c));
-    const float4 is = __ldg(reinterpret_cast<const float4 *>(invstd + c));
-    const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c));
-    const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + c));
-    float4 o;
-    o.x = (v.x - mu.x) * is.x * g.x + b.x;
-    o.y = (v.y - mu.y) * is.y * g.y + b.y;
-    o.z = (v.z - mu.z) * is.z * g.z + b.z;
-    o.w = (v.w - mu.w) * is.w * g.w + b.w;
-    if (RELU) {
-        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+    const int c = cx * 4;
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
+    const float4 sc = make_float4(is.x * g.x, is.y * g.y, is.z * g.z, is.w * g.w);
+    const float4 sh = make_float4(b.x - mu.x * sc.x, b.y - mu.y * sc.y, b.z - mu.z * sc.z, b.w - mu.w * sc.w);
+    const int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK;
+    const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
+    auto f = [&](float4 v) {
+        float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+        if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        return o;
+    };
+    int64_t r = r0 + ry;
+    for (; r + 3 * ty < r1; r += 4 * ty) {
+        const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
+        const float4 v2 = __ldg(x + (r + 2 * ty) * tx + cx), v3 = __ldg(x + (r + 3 * ty) * tx + cx);
+        y[r * tx + cx] = f(v0); y[(r + ty) * tx + cx] = f(v1);
+        y[(r + 2 * ty) * tx + cx] = f(v2); y[(r + 3 * ty) * tx + cx] = f(v3);
     }
-    y[i] = o;
+    for (; r < r1; r += ty) y[r * tx + cx] = f(__ldg(x + r * tx + cx));
 }
 
 // dsum[c] += sum dz ; dsum[C + c] += sum dz * xhat     (dz = dy masked by the recomputed ReLU)
@@ -110,80 +127,69 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4 *__rest
                                                             const float *__restrict__ beta, double *__restrict__ dsum) {
     extern __shared__ float4 s_red[];
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+    const int c = cx * 4;
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
     const int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK;
     const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ry < ty) {
-        const int c = cx * 4;
-        const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean + c));
-        const float4 is = __ldg(reinterpret_cast<const float4 *>(invstd + c));
-        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c));
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + c));
-        for (int64_t r = r0 + ry; r < r1; r += ty) {
-            const float4 v = __ldg(x + r * tx + cx);
-            float4 d = __ldg(dy + r * tx + cx);
-            const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
-            if (RELU) {
-                if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
-                if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
-                if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
-                if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
-            }
-            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
-            q.x += d.x * h.x; q.y += d.y * h.y; q.z += d.z * h.z; q.w += d.w * h.w;
+    auto f = [&](float4 v, float4 d) {
+        const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
+        if (RELU) {
+            if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
+            if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
+            if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
+            if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
         }
-        s_red[ry * tx + cx] = s;
-        s_red[(ty + ry) * tx + cx] = q;
+        acc4(s, d);
+        q.x += d.x * h.x; q.y += d.y * h.y; q.z += d.z * h.z; q.w += d.w * h.w;
+    };
+    int64_t r = r0 + ry;
+    for (; r + ty < r1; r += 2 * ty) {
+        const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
+        const float4 d0 = __ldg(dy + r * tx + cx), d1 = __ldg(dy + (r + ty) * tx + cx);
+        f(v0, d0); f(v1, d1);
     }
-    __syncthreads();
-    if (ry == 0) {
-        for (int j = 1; j < ty; j++) {
-            const float4 a = s_red[j * tx + cx], b2 = s_red[(ty + j) * tx + cx];
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-            q.x += b2.x; q.y += b2.y; q.z += b2.z; q.w += b2.w;
-        }
-        const int C = tx * 4, c = cx * 4;
-        atomicAdd(dsum + c + 0, (double)s.x); atomicAdd(dsum + c + 1, (double)s.y);
-        atomicAdd(dsum + c + 2, (double)s.z); atomicAdd(dsum + c + 3, (double)s.w);
-        atomicAdd(dsum + C + c + 0, (double)q.x); atomicAdd(dsum + C + c + 1, (double)q.y);
-        atomicAdd(dsum + C + c + 2, (double)q.z); atomicAdd(dsum + C + c + 3, (double)q.w);
-    }
+    for (; r < r1; r += ty) f(__ldg(x + r * tx + cx), __ldg(dy + r * tx + cx));
+    block_reduce_to_global(s, q, tx, ty, cx, ry, s_red, dsum);
 }
 
 // dx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat)), means over the GLOBAL count
 template <bool RELU>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ x,
-                                                           int64_t n4, int tx, const float *__restrict__ mean,
+                                                           int64_t n, int tx, int ty, const float *__restrict__ mean,
                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                            const float *__restrict__ beta, const double *__restrict__ dsum,
                                                            const double *__restrict__ count, float4 *__restrict__ dx) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int C = tx * 4, c = (int)(i % tx) * 4;
+    const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+    const int C = tx * 4, c = cx * 4;
     const double inv_count = *count > 0.0 ? 1.0 / *count : 0.0;
-    const float4 v = __ldg(x + i);
-    float4 d = __ldg(dy + i);
-    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean + c));
-    const float4 is = __ldg(reinterpret_cast<const float4 *>(invstd + c));
-    const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c));
-    const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
-    if (RELU) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + c));
-        if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
-        if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
-        if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
-        if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
+    const float4 a = make_float4((float)(dsum[c] * inv_count), (float)(dsum[c + 1] * inv_count),
+                                 (float)(dsum[c + 2] * inv_count), (float)(dsum[c + 3] * inv_count));
+    const float4 bb = make_float4((float)(dsum[C + c] * inv_count), (float)(dsum[C + c + 1] * inv_count),
+                                  (float)(dsum[C + c + 2] * inv_count), (float)(dsum[C + c + 3] * inv_count));
+    const float4 gi = make_float4(g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w);
+    const int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK;
+    const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
+    auto f = [&](float4 v, float4 d) {
+        const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
+        if (RELU) {
+            if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
+            if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
+            if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
+            if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
+        }
+        return make_float4(gi.x * (d.x - a.x - h.x * bb.x), gi.y * (d.y - a.y - h.y * bb.y), gi.z * (d.z - a.z - h.z * bb.z),
+                           gi.w * (d.w - a.w - h.w * bb.w));
+    };
+    int64_t r = r0 + ry;
+    for (; r + ty < r1; r += 2 * ty) {
+        const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
+        const float4 d0 = __ldg(dy + r * tx + cx), d1 = __ldg(dy + (r + ty) * tx + cx);
+        dx[r * tx + cx] = f(v0, d0);
+        dx[(r + ty) * tx + cx] = f(v1, d1);
     }
-    const float a0 = (float)(dsum[c + 0] * inv_count), a1 = (float)(dsum[c + 1] * inv_count);
-    const float a2 = (float)(dsum[c + 2] * inv_count), a3 = (float)(dsum[c + 3] * inv_count);
-    const float b0 = (float)(dsum[C + c + 0] * inv_count), b1 = (float)(dsum[C + c + 1] * inv_count);
-    const float b2 = (float)(dsum[C + c + 2] * inv_count), b3 = (float)(dsum[C + c + 3] * inv_count);
-    float4 o;
-    o.x = g.x * is.x * (d.x - a0 - h.x * b0);
-    o.y = g.y * is.y * (d.y - a1 - h.y * b1);
-    o.z = g.z * is.z * (d.z - a2 - h.z * b2);
-    o.w = g.w * is.w * (d.w - a3 - h.w * b3);
-    dx[i] = o;
+    for (; r < r1; r += ty) dx[r * tx + cx] = f(__ldg(x + r * tx + cx), __ldg(dy + r * tx + cx));
 }
 
 }  // namespace
@@ -216,12 +222,12 @@ extern "C" int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *s
                                                          running_var);
     U2_LAUNCH_OK();
     if (n == 0) return 0;
-    const int64_t n4 = n * (C / 4);
-    const unsigned grid = (unsigned)u2_ceil_div(n4, 256);
+    const BnGeom g = bn_geom(C);
+    const unsigned grid = (unsigned)u2_ceil_div(n, BN_ROWS_PER_BLOCK);
     if (relu)
-        bn_apply_kernel<true><<<grid, 256, 0, st>>>((const float4 *)x, n4, C / 4, save_mean, save_invstd, gamma, beta, (float4 *)y);
+        bn_apply_kernel<true><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y);
     else
-        bn_apply_kernel<false><<<grid, 256, 0, st>>>((const float4 *)x, n4, C / 4, save_mean, save_invstd, gamma, beta, (float4 *)y);
+        bn_apply_kernel<false><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y);
     U2_LAUNCH_OK();
     return 0;
 }
@@ -255,14 +261,14 @@ extern "C" int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(u2_bn_supported(C), "u2_bn_bwd_apply: C=%d", C);
     if (n == 0) return 0;
-    const int64_t n4 = n * (C / 4);
-    const unsigned grid = (unsigned)u2_ceil_div(n4, 256);
+    const BnGeom g = bn_geom(C);
+    const unsigned grid = (unsigned)u2_ceil_div(n, BN_ROWS_PER_BLOCK);
     if (relu)
-        bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>((const float4 *)dy, (const float4 *)x, n4, C / 4, mean, invstd, gamma,
-                                                        beta, dsum, count_dev, (float4 *)dx);
+        bn_bwd_apply_kernel<true><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd,
+                                                                 gamma, beta, dsum, count_dev, (float4 *)dx);
     else
-        bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>((const float4 *)dy, (const float4 *)x, n4, C / 4, mean, invstd, gamma,
-                                                         beta, dsum, count_dev, (float4 *)dx);
+        bn_bwd_apply_kernel<false><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd,
+                                                                  gamma, beta, dsum, count_dev, (float4 *)dx);
     U2_LAUNCH_OK();
     return 0;
 }
