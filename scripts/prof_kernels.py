@@ -38,11 +38,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default="all")
-    ap.add_argument("--math", default="tf32")
+    ap.add_argument("--math", default="bf16")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) \
         if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
-    hbm, tf32 = peaks["hbm_gbs"], peaks["bf16_tflops"] / 2
+    hbm, tf32 = peaks["hbm_gbs"], peaks["bf16_tflops"] / (1 if args.math == "bf16" else 2)
     ops.set_math(args.math)
     coords, feats = scans.make_batch([0, 1], "nusc", 5, 0.05)
     c = torch.from_numpy(coords).cuda()
@@ -56,7 +56,7 @@ def main():
             r["hbm_frac"] = round(bytes_ / ms / 1e6 / hbm, 3)
         if flops is not None:
             r["TFLOP/s"] = round(flops / ms / 1e9, 1)
-            r["tf32_frac"] = round(flops / ms / 1e9 / tf32, 3)
+            r["tensor_frac"] = round(flops / ms / 1e9 / tf32, 3)
         r["note"] = note
         rows.append(r)
         print(json.dumps(r), flush=True)
@@ -83,19 +83,21 @@ def main():
             x = torch.randn(n, cin, device="cuda")
             w = torch.randn(27, cin, cout, device="cuda") * 0.05
             g = torch.randn(n, cout, device="cuda")
+            mth = ops._state["math"]
+            xo, go = (ops.cast_bf16(x), ops.cast_bf16(g)) if mth == 2 else (x, g)
             fl = 2.0 * M * cin * cout
             by = (n * cin + n * cout + 27 * cin * cout) * 4 + 4 * 27 * n
-            report(f"conv_fwd k3 {cin}->{cout} n={n} M={M}", timeit(lambda: ops._conv_gather_gemm("fwd", km, x, w, False, km.nbr, n, cout, ops._state["math"], side=False), args.reps),
+            report(f"conv_fwd k3 {cin}->{cout} n={n} M={M}", timeit(lambda: ops._conv_gather_gemm("fwd", km, xo, w, False, km.nbr, n, cout, mth, side=False), args.reps),
                    bytes_=by, flops=fl)
-            report(f"conv_dgrad k3 {cout}->{cin}", timeit(lambda: ops._conv_gather_gemm("dgrad", km, g, w, True, km.nbrT, n, cin, ops._state["math"], side=True), args.reps),
+            report(f"conv_dgrad k3 {cout}->{cin}", timeit(lambda: ops._conv_gather_gemm("dgrad", km, go, w, True, km.nbrT, n, cin, mth, side=True), args.reps),
                    bytes_=by, flops=fl)
             flat = km.flat_pairs
             dw = torch.empty_like(w)
             st = torch.cuda.current_stream().cuda_stream
             if ops._state["math"] != 0:
                 report(f"conv_wgrad k3 {cin}x{cout}", timeit(lambda: _lib.check(_lib.lib().u2_conv_wgrad_pairs(
-                    x.data_ptr(), cin, g.data_ptr(), cout, km.nbr.data_ptr(), km.nbr.shape[1], n, 27, flat.data_ptr(),
-                    km.nbsizes.data_ptr(), 0, dw.data_ptr(), ops._state["math"], st)), args.reps),
+                    xo.data_ptr(), cin, go.data_ptr(), cout, km.nbr.data_ptr(), km.nbr.shape[1], n, 27, flat.data_ptr(),
+                    km.nbsizes.data_ptr(), 0, dw.data_ptr(), mth, st)), args.reps),
                     bytes_=(n * cin + n * cout + 27 * cin * cout) * 4 + 8 * M, flops=fl)
 
     if args.only in ("all", "pv"):

@@ -58,6 +58,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// experiment variants (U2_CPASYNC_MODE): 1 = .ca (allocate in L1), 2 = .cg + L2::128B prefetch, 3 = .cg + L2::256B
+__device__ __forceinline__ void cp_async16_mode(uint32_t dst, const void *src, uint32_t src_bytes, int mode) {
+    if (mode == 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    else if (mode == 2) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    else if (mode == 3) asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -153,6 +160,7 @@ struct FwdParams {
     int64_t ld, n_dst;
     int Cs, Cd, K, NT, stages, tmem_cols;
     long long *dbg;  // optional per-CTA phase timestamps (U2_DEBUG_CONV_TIMING)
+    int cp_mode;
 };
 
 // ROWB = bytes of one gathered row per pipeline stage (128 or 64): 32/16 fp32 or 64/32 bf16 channels.
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
 #pragma unroll
                 for (int i = 0; i < CHUNKS; i++) {
                     const bool ok = off[i] != 0xFFFFFFFFu;
-                    cp_async16(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u);
+                    cp_async16_mode(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u, p.cp_mode);
                 }
                 cp_async_mbar_arrive_noinc(s_full + s);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -881,7 +889,7 @@ struct WgradParams {
     const int *nbsizes;
     float *dW;
     int64_t ld;
-    int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt;
+    int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt, cp_mode;
 };
 
 template <bool BF16>
@@ -965,7 +973,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
                 const int arow = pairs[r].x;
                 const bool ok = arow >= 0 && a_ch_ok;
                 const uint8_t *src = p.X + (ok ? (size_t)arow * a_pitch + (size_t)a_ch * G::ES : 0);
-                cp_async16(a_base + a_atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u);
+                cp_async16_mode(a_base + a_atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u, p.cp_mode);
             }
             // B: units (channel atom, 32-row block) w, w+4, ...
             for (int u = warp; u < n_batoms * G::RB; u += 4) {
@@ -978,7 +986,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
                     const int brow = pairs[r].y;
                     const bool ok = brow >= 0 && ch_ok;
                     const uint8_t *src = p.dY + (ok ? (size_t)brow * b_pitch + (size_t)(n0 + ch) * G::ES : 0);
-                    cp_async16(b_base + atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u);
+                    cp_async16_mode(b_base + atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u, p.cp_mode);
                 }
             }
             cp_async_mbar_arrive_noinc(s_full + s);
@@ -1130,6 +1138,8 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     FwdParams p;
     p.X = (const uint8_t *)X; p.Wt = (const uint8_t *)scratch; p.table = table; p.perm = perm; p.Y = Y;
     p.dbg = nullptr;
+    static const int cp_mode = getenv("U2_CPASYNC_MODE") ? atoi(getenv("U2_CPASYNC_MODE")) : 1;  // .ca measured 15-25 % faster
+    p.cp_mode = cp_mode;
     p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
     int cols = 32;
     while (cols < NT) cols <<= 1;
@@ -1174,6 +1184,8 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     WgradParams p;
     p.X = (const uint8_t *)X; p.dY = (const uint8_t *)dY; p.nbr = nbr; p.flat = flat; p.nbsizes = nbsizes; p.dW = dW;
     p.ld = ld; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT; p.swap = swap;
+    static const int cp_mode_w = getenv("U2_CPASYNC_MODE_W") ? atoi(getenv("U2_CPASYNC_MODE_W")) : 1;
+    p.cp_mode = cp_mode_w;
     p.n_mt = (Cs + TILE_M - 1) / TILE_M;
     p.n_nt = Cd / NT;
     int cols = 32;

@@ -52,20 +52,23 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float4 *__restrict_
                                                        double *__restrict__ sums) {
     extern __shared__ float4 s_red[];  // [2][ty][tx]
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
-    const int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK;
-    const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
     if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * tx * 4] = (double)n;  // local row count rides along
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t r = r0 + ry;
-    for (; r + 3 * ty < r1; r += 4 * ty) {
-        const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
-        const float4 v2 = __ldg(x + (r + 2 * ty) * tx + cx), v3 = __ldg(x + (r + 3 * ty) * tx + cx);
-        acc4(s, v0); acc4sq(q, v0); acc4(s, v1); acc4sq(q, v1);
-        acc4(s, v2); acc4sq(q, v2); acc4(s, v3); acc4sq(q, v3);
-    }
-    for (; r < r1; r += ty) {
-        const float4 v = __ldg(x + r * tx + cx);
-        acc4(s, v); acc4sq(q, v);
+    // grid-stride over 128-row blocks: per-address fp64 atomics serialise in L2, so a CTA keeps its
+    // partial sums in registers over all of its blocks and reduces once
+    for (int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK; r0 < n; r0 += (int64_t)gridDim.x * BN_ROWS_PER_BLOCK) {
+        const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
+        int64_t r = r0 + ry;
+        for (; r + 3 * ty < r1; r += 4 * ty) {
+            const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
+            const float4 v2 = __ldg(x + (r + 2 * ty) * tx + cx), v3 = __ldg(x + (r + 3 * ty) * tx + cx);
+            acc4(s, v0); acc4sq(q, v0); acc4(s, v1); acc4sq(q, v1);
+            acc4(s, v2); acc4sq(q, v2); acc4(s, v3); acc4sq(q, v3);
+        }
+        for (; r < r1; r += ty) {
+            const float4 v = __ldg(x + r * tx + cx);
+            acc4(s, v); acc4sq(q, v);
+        }
     }
     block_reduce_to_global(s, q, tx, ty, cx, ry, s_red, sums);
 }
@@ -129,8 +132,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4 *__rest
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
     const int c = cx * 4;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
-    const int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK;
-    const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
     auto f = [&](float4 v, float4 d) {
         const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
@@ -143,13 +144,16 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4 *__rest
         acc4(s, d);
         q.x += d.x * h.x; q.y += d.y * h.y; q.z += d.z * h.z; q.w += d.w * h.w;
     };
-    int64_t r = r0 + ry;
-    for (; r + ty < r1; r += 2 * ty) {
-        const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
-        const float4 d0 = __ldg(dy + r * tx + cx), d1 = __ldg(dy + (r + ty) * tx + cx);
-        f(v0, d0); f(v1, d1);
+    for (int64_t r0 = (int64_t)blockIdx.x * BN_ROWS_PER_BLOCK; r0 < n; r0 += (int64_t)gridDim.x * BN_ROWS_PER_BLOCK) {
+        const int64_t r1 = min(n, r0 + BN_ROWS_PER_BLOCK);
+        int64_t r = r0 + ry;
+        for (; r + ty < r1; r += 2 * ty) {
+            const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
+            const float4 d0 = __ldg(dy + r * tx + cx), d1 = __ldg(dy + (r + ty) * tx + cx);
+            f(v0, d0); f(v1, d1);
+        }
+        for (; r < r1; r += ty) f(__ldg(x + r * tx + cx), __ldg(dy + r * tx + cx));
     }
-    for (; r < r1; r += ty) f(__ldg(x + r * tx + cx), __ldg(dy + r * tx + cx));
     block_reduce_to_global(s, q, tx, ty, cx, ry, s_red, dsum);
 }
 
@@ -205,7 +209,9 @@ extern "C" int u2_bn_stats(const float *x, int64_t n, int32_t C, double *sums, u
     if (n == 0) return 0;
     const BnGeom g = bn_geom(C);
     const int threads = g.tx * g.ty;
-    bn_stats_kernel<<<(unsigned)u2_ceil_div(n, BN_ROWS_PER_BLOCK), threads, 2 * threads * sizeof(float4), st>>>(
+    int64_t blocks = u2_ceil_div(n, BN_ROWS_PER_BLOCK);
+    if (blocks > 4 * U2_NUM_SMS) blocks = 4 * U2_NUM_SMS;  // 4 CTAs of 256 threads per SM, each reduces once
+    bn_stats_kernel<<<(unsigned)blocks, threads, 2 * threads * sizeof(float4), st>>>(
         (const float4 *)x, n, g.tx, g.ty, sums);
     U2_LAUNCH_OK();
     return 0;
@@ -243,7 +249,9 @@ extern "C" int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int3
     if (n == 0) return 0;
     const BnGeom g = bn_geom(C);
     const int threads = g.tx * g.ty;
-    const unsigned grid = (unsigned)u2_ceil_div(n, BN_ROWS_PER_BLOCK);
+    int64_t blocks = u2_ceil_div(n, BN_ROWS_PER_BLOCK);
+    if (blocks > 4 * U2_NUM_SMS) blocks = 4 * U2_NUM_SMS;
+    const unsigned grid = (unsigned)blocks;
     const size_t smem = 2 * threads * sizeof(float4);
     if (relu)
         bn_bwd_reduce_kernel<true><<<grid, threads, smem, st>>>((const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean,
