@@ -331,13 +331,27 @@ def run_ours(args, w):
         pk = peaks()
         summ = timer.summary()
         tot_ms = sum(d["ms"] for d in summ.values())
-        dom_kind = max(summ, key=lambda k: summ[k]["ms"])
-        dom = summ[dom_kind]
-        # conv GEMMs are the only dense contraction: bound = tensor pipe; tf32 peak = 1/2 bf16
+        # fwd and dgrad are the SAME kernel (conv_fwd_tc_kernel over the two neighbour tables): one class
+        classes = {"conv_fwd_tc_kernel (fwd+dgrad)": [k for k in ("fwd", "dgrad") if k in summ],
+                   "conv_wgrad_tc_kernel (wgrad)": [k for k in ("wgrad",) if k in summ]}
+        agg = {name: {f: sum(summ[k][f] for k in ks) for f in ("launches", "ms", "flops")} for name, ks in classes.items() if ks}
+        dom_name = max(agg, key=lambda k: agg[k]["ms"])
+        dom = agg[dom_name]
+        # conv GEMMs are the only dense contraction: bound = tensor pipe; tf32 peak = 1/2 bf16 (BASELINE.md par. 2)
         peak_tf = (pk["bf16_sus"] if math == "bf16" else pk["bf16_sus"] / 2.0)  # fp32 FFMA mode is reported against tf32 too
         achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": f"sparse_conv_{dom_kind}", "achieved": achieved, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+        if os.path.exists(tpath) and math == "bf16":
+            tk = json.load(open(tpath))["kernels"]
+            key = "conv_fwd_tc_kernel<128, 1>" if dom_name.startswith("conv_fwd") else "conv_wgrad_tc_kernel<1>"
+            if key in tk:
+                traffic = tk[key]["dram_bytes_per_launch"]
+        roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write per launch, ncu launch list profiles/r1_launches_bf16.csv (average over "
+                                    "the kernel's launches of one step)" if traffic else None,
+                    "flops_per_launch": dom["flops"] / dom["launches"],
                     "peak_source": f"{pk['src']} bf16 sustained" + ("" if math == "bf16" else " / 2 (tf32)"),
                     "launches_per_step": dom["launches"] / args.steps,
                     "avg_launch_ms": dom["ms"] / dom["launches"],
