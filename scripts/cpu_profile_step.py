@@ -4,11 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from u2mkd_b200 import models, ops, scans
 import u2mkd_b200.torchsparse as ts
-ops.set_math("tf32")
+ops.set_math("bf16")
 torch.backends.cuda.matmul.allow_tf32 = True
 w = scans.WORKLOADS["nusc5_cr2.0_b2"]
 dev = torch.device("cuda")
 net = models.product().SPVCNN(cr=w["cr"], pres=w["voxel_size"], vres=w["voxel_size"]).to(dev)
+from u2mkd_b200 import fusion
+fusion.optimize(net)
 opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)
 c, f = scans.make_batch([0, 1], w["kind"], w["sweeps"], w["voxel_size"])
 c, f = torch.from_numpy(c).to(dev), torch.from_numpy(f).to(dev)
@@ -35,5 +37,8 @@ for _ in range(3): step()
 pr.disable()
 torch.cuda.synchronize()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(40)
-print(s.getvalue()[:9000])
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(45)
+print(s.getvalue()[:12000])
+s2 = io.StringIO()
+pstats.Stats(pr, stream=s2).sort_stats("cumulative").print_stats(40)
+print(s2.getvalue()[:9000])

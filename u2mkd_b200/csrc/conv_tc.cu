@@ -889,7 +889,7 @@ struct WgradParams {
     const int *nbsizes;
     float *dW;
     int64_t ld;
-    int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt, cp_mode;
+    int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt, cp_mode, TM;
 };
 
 template <bool BF16>
@@ -899,7 +899,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     const int NT = p.NT;
     const int n_batoms = (NT + G::CPA - 1) / G::CPA;
     const int B_BYTES = n_batoms * G::ATOM;
-    const int stage_bytes = G::A_BYTES + B_BYTES;
+    const int TM = p.TM;                          // 128-channel input slices per CTA (accumulators side by side in TMEM)
+    const int A_BYTES = TM * G::A_BYTES;
+    const int stage_bytes = A_BYTES + B_BYTES;
     int2 *s_pairs = reinterpret_cast<int2 *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *s_full = reinterpret_cast<uint64_t *>(s_pairs + WG_PAIRS);
     uint64_t *s_empty = s_full + MAX_STAGES;
@@ -908,7 +910,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = blockIdx.y;
-    const int mt = blockIdx.z / p.n_nt, nt = blockIdx.z % p.n_nt;
+    const int mt = (blockIdx.z / p.n_nt) * p.TM, nt = blockIdx.z % p.n_nt;  // first input slice of this CTA
     // pair range of this CTA (all threads compute the same scalar prefix over <= 32 sizes)
     int koff = 0;
     for (int j = 0; j < k; j++) koff += __ldg(p.nbsizes + j);
@@ -955,25 +957,27 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
         // ============================ producers: gather both operands ============================
         const int cc = lane & 7;     // 16-byte chunk inside a 128-byte atom row
         const int rsub = lane >> 3;  // pair inside a group of 4
-        // A: warp w owns unit w = (channel atom, 32-row block)
-        const int a_atom = warp / G::RB, a_rb = warp % G::RB;
-        const int a_ch = m0 + a_atom * G::CPA + cc * (16 / G::ES);
-        const bool a_ch_ok = a_ch < p.Cs;
         const size_t a_pitch = (size_t)p.Cs * G::ES, b_pitch = (size_t)p.Cd * G::ES;
         for (int it = 0; it < n_items; it++) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(s_empty + s, ph ^ 1u);
             const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t b_base = a_base + G::A_BYTES;
+            const uint32_t b_base = a_base + A_BYTES;
             const int2 *pairs = s_pairs + it * G::KR;
+            // A: units (input slice, channel atom, 32-row block) w, w+4, ...
+            for (int u = warp; u < TM * G::A_ATOMS * G::RB; u += 4) {
+                const int a_atom = u / G::RB, a_rb = u % G::RB;  // a_atom counts atoms across the TM slices
+                const int a_ch = m0 + a_atom * G::CPA + cc * (16 / G::ES);
+                const bool a_ch_ok = a_ch < p.Cs;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int r = a_rb * 32 + 4 * i + rsub;
-                const int arow = pairs[r].x;
-                const bool ok = arow >= 0 && a_ch_ok;
-                const uint8_t *src = p.X + (ok ? (size_t)arow * a_pitch + (size_t)a_ch * G::ES : 0);
-                cp_async16_mode(a_base + a_atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u, p.cp_mode);
+                for (int i = 0; i < 8; i++) {
+                    const int r = a_rb * 32 + 4 * i + rsub;
+                    const int arow = pairs[r].x;
+                    const bool ok = arow >= 0 && a_ch_ok;
+                    const uint8_t *src = p.X + (ok ? (size_t)arow * a_pitch + (size_t)a_ch * G::ES : 0);
+                    cp_async16_mode(a_base + a_atom * G::ATOM + r * 128 + G::swz(cc, r) * 16, src, ok ? 16u : 0u, p.cp_mode);
+                }
             }
             // B: units (channel atom, 32-row block) w, w+4, ...
             for (int u = warp; u < n_batoms * G::RB; u += 4) {
@@ -994,18 +998,21 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
         // ============================ epilogue: reduce the tile into dW[k] ============================
         mbar_wait(s_accum, 0);
         tc_fence_after();
-        const int ci = m0 + warp * 32 + lane;  // accumulator row (TMEM lane) = input channel
-        float *out = p.dW + ((int64_t)k * p.Cs + ci) * p.Cd + n0;
-        for (int c = 0; c < NT; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-            tmem_ld_wait();
-            if (ci < p.Cs) {
+        for (int tm = 0; tm < TM; tm++) {
+            const int ci = m0 + tm * TILE_M + warp * 32 + lane;  // accumulator row (TMEM lane) = input channel
+            if (m0 + tm * TILE_M >= p.Cs) break;
+            float *out = p.dW + ((int64_t)k * p.Cs + ci) * p.Cd + n0;
+            for (int c = 0; c < NT; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tm * NT + c), v);
+                tmem_ld_wait();
+                if (ci < p.Cs) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + j), "f"(__uint_as_float(v[j])),
-                                 "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                                 : "memory");
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + j), "f"(__uint_as_float(v[j])),
+                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                }
             }
         }
     } else if (warp == 5) {
@@ -1019,12 +1026,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
             proxy_fence_async();
             if (lane == 0) {
                 const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_base = a_base + G::A_BYTES;
+                const uint32_t b_base = a_base + A_BYTES;
+                for (int tm = 0; tm < TM; tm++) {
+                    if (m0 + tm * TILE_M >= p.Cs) break;
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const uint64_t ad = make_smem_desc(a_base + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
-                    const uint64_t bd = make_smem_desc(b_base + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
-                    umma<BF16>(tmem_base, ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                    for (int g = 0; g < 4; g++) {
+                        const uint64_t ad = make_smem_desc(a_base + tm * G::A_BYTES + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
+                        const uint64_t bd = make_smem_desc(b_base + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
+                        umma<BF16>(tmem_base + (uint32_t)(tm * NT), ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(s_empty + s);
                 if (it == n_items - 1) umma_commit(s_accum);
@@ -1188,21 +1198,29 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     p.cp_mode = cp_mode_w;
     p.n_mt = (Cs + TILE_M - 1) / TILE_M;
     p.n_nt = Cd / NT;
-    int cols = 32;
-    while (cols < NT) cols <<= 1;
-    p.tmem_cols = cols;
     const int cpa = bf16 ? 64 : 32, atom = bf16 ? 8192 : 4096;
-    const size_t stage_bytes = (size_t)(TILE_M / cpa + (NT + cpa - 1) / cpa) * atom;
     const size_t fixed = (size_t)WG_PAIRS * sizeof(int2) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
     const size_t budget = 227 * 1024;
-    int stages = (int)((budget / 2 - fixed - 1024) / stage_bytes);
+    // input slices per CTA: every slice re-gathers the dY rows, so take as many as TMEM (512 columns)
+    // and shared memory (>= 3 stages) allow
+    static const int tm_max = getenv("U2_WGRAD_TM") ? atoi(getenv("U2_WGRAD_TM")) : 4;
+    int TM = p.n_mt < tm_max ? p.n_mt : tm_max;
+    while (TM > 1 && (TM * NT > 512 ||
+                      (budget - fixed) / ((size_t)(TM * (TILE_M / cpa) + (NT + cpa - 1) / cpa) * atom) < 3))
+        TM--;
+    p.TM = TM;
+    int cols = 32;
+    while (cols < TM * NT) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = (size_t)(TM * (TILE_M / cpa) + (NT + cpa - 1) / cpa) * atom;
+    int stages = cols <= 256 ? (int)((budget / 2 - fixed - 1024) / stage_bytes) : 0;
     if (stages < 3) stages = (int)((budget - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     U2_CHECK_ARG(stages >= 2, "u2_conv_wgrad_tc: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + fixed;
     // a single offset has at most n_rows pairs (one per row of the table's row side)
-    dim3 grid((unsigned)u2_ceil_div(n_rows, WG_PAIRS), (unsigned)K, (unsigned)(p.n_mt * p.n_nt));
+    dim3 grid((unsigned)u2_ceil_div(n_rows, WG_PAIRS), (unsigned)K, (unsigned)(u2_ceil_div(p.n_mt, TM) * p.n_nt));
     if (bf16) {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_wgrad_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
