@@ -107,6 +107,17 @@ class ConvTimer:
         # neighbour tables per step and push the caching allocator into cudaMalloc every step
         self.items.append((kind, kmap.nbsizes, n_dst, K, c_src, c_dst, e0, e1))
 
+    def by_shape(self, steps):
+        """ms per step grouped by (kind, K, c_src, c_dst, n_dst): where the conv time goes."""
+        out = {}
+        for kind, nbsizes, n_dst, K, cs, cd, e0, e1 in self.items:
+            d = out.setdefault((kind, K, cs, cd, n_dst), [0, 0.0])
+            d[0] += 1
+            d[1] += e0.elapsed_time(e1)
+        rows = sorted(out.items(), key=lambda kv: -kv[1][1])
+        return [f"{k[0]:6s} K={k[1]:2d} {k[2]:4d}->{k[3]:4d} n_dst={k[4]:7d} x{v[0] // steps:3d}/step {v[1] / steps:7.3f} ms/step"
+                for k, v in rows]
+
     def summary(self):
         """per kind: launches, total ms, algorithmic flops (2*M*Cs*Cd over REAL pairs only)."""
         out, pairs_cache = {}, {}
@@ -359,6 +370,8 @@ def run_ours(args, w):
                     "all_conv": {k: {"ms_per_step": d["ms"] / args.steps, "tflops": d["flops"] / (d["ms"] / 1e3) / 1e12}
                                  for k, d in summ.items()},
                     "conv_share_of_step": tot_ms / ms}
+        if os.environ.get("U2_BENCH_LAYERS"):
+            print("\n".join(timer.by_shape(args.steps)[:40]), file=sys.stderr)
         line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": math, "data": "synthetic",
