@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size")
     ap.add_argument("--no-fusion", action="store_true", help="keep torch BatchNorm/ReLU modules unfused")
+    ap.add_argument("--no-conv-bn", action="store_true", help="BatchNorm as its own node after each conv (A/B of the conv+BN fusion)")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu launch lists): no allocator pre-pass, no e2e region, no CPU baseline")
     return ap.parse_args()
@@ -262,7 +263,7 @@ def run_ours(args, w):
         net = fam.SparseSyncBatchNorm.convert_sync_batchnorm(net)  # train_spformer.py:79
     if not args.no_fusion:
         from u2mkd_b200 import fusion
-        fusion.optimize(net)  # same module tree / parameters; BN(+ReLU) run the fused kernels
+        fusion.optimize(net, fuse_conv_bn=not args.no_conv_bn)  # same module tree / parameters; BN(+ReLU) run the fused kernels
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.bucket_mb)  # train_spformer.py:82-83
@@ -380,6 +381,7 @@ def run_ours(args, w):
                            "params": n_params, "optimizer": "sgd-nesterov", "loss": "cross_entropy",
                            "parallelism": f"dp{world}" + ("" if world == 1 or args.no_sync_bn else "+syncbn"),
                            "fused_bn_relu": not args.no_fusion,
+                           "fused_conv_bn": not (args.no_fusion or args.no_conv_bn),
                            "l2": "activations (>1 GB/step) exceed the 126 MB L2; a different scan batch every step"},
                 "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},

@@ -188,6 +188,27 @@ int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const
                     const float *gamma, const float *beta, const double *dsum, const double *count_dev, int32_t relu,
                     float *dx, u2_stream_t stream);
 
+/* ---- conv -> BatchNorm(+ReLU) fusion (the Sequential(Conv3d, BatchNorm, ReLU) triples of
+ * core/models/build_blocks.py:21-84).  u2_conv_fwd_stats = u2_conv_fwd / u2_conv_fwd_perm (perm may be NULL) whose epilogue
+ * also stores, per warp of each 128-row tile, the column sums and sums of squares of Y:
+ * tile_stats fp32 [u2_conv_tile_stats_parts(rows)][2][Cd], rows = ld with perm, n_dst without; needs Cd tiles % 32 == 0.
+ * u2_bn_stats_from_tiles folds them into the fp64 [2C+1] sums buffer of u2_bn_apply (no pass over Y).
+ * The *_dual variants also emit the bf16 copy the next conv (forward) / the conv backward consumes, so that
+ * no separate u2_cast_bf16 pass is needed; in u2_bn_bwd_apply_dual either output may be NULL.                     */
+size_t u2_conv_tile_stats_parts(int64_t rows);
+int u2_conv_fwd_stats(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
+                      const int32_t *table, const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd,
+                      float *Y, int32_t math, void *scratch, size_t scratch_bytes, float *tile_stats,
+                      size_t tile_stats_bytes, u2_stream_t stream);
+int u2_bn_stats_from_tiles(const float *tile_stats, int64_t n_parts, int32_t C, int64_t n, double *sums,
+                           u2_stream_t stream);
+int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
+                     const float *gamma, const float *beta, int32_t relu, float *y, void *y_bf16, float *save_mean,
+                     float *save_invstd, float *running_mean, float *running_var, u2_stream_t stream);
+int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
+                         const float *gamma, const float *beta, const double *dsum, const double *count_dev,
+                         int32_t relu, float *dx, void *dx_bf16, u2_stream_t stream);
+
 /* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
 int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);
 

@@ -13,7 +13,7 @@ w = scans.WORKLOADS["nusc5_cr2.0_b2"]
 dev = torch.device("cuda")
 net = models.product().SPVCNN(cr=w["cr"], pres=w["voxel_size"], vres=w["voxel_size"]).to(dev)
 from u2mkd_b200 import fusion
-if "--no-fusion" not in sys.argv: fusion.optimize(net)
+if "--no-fusion" not in sys.argv: fusion.optimize(net, fuse_conv_bn="--no-conv-bn" not in sys.argv)
 opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)
 pool = []
 for i in range(2):

@@ -13,7 +13,7 @@ size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd
 int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
-                   void *scratch, size_t scratch_bytes, cudaStream_t st);
+                   void *scratch, size_t scratch_bytes, float *tile_stats, cudaStream_t st);
 int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
 int u2_conv_fwd_mt(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
                    const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
@@ -59,7 +59,7 @@ extern "C" int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const floa
     if (math == U2_MATH_FP32) return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #ifdef U2_WITH_TC
     if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math))
-        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, nullptr, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, st);
+        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, nullptr, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, nullptr, st);
     U2_CHECK_ARG(math != U2_MATH_BF16, "u2_conv_fwd: shape Cs=%d Cd=%d K=%d has no bf16 kernel (caller must use TF32/FP32)", Cs, Cd, K);
     if (math == U2_MATH_TF32)  // shapes the MMA tiles cannot hold (e.g. the Cs = 4 stem conv)
         return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
@@ -119,7 +119,7 @@ extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const
                  "u2_conv_fwd_perm: unsupported shape/math");
     if (math == U2_MATH_BF16)
         return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
-                              (cudaStream_t)stream);
+                              nullptr, (cudaStream_t)stream);
     static const int use_tma = getenv("U2_NO_TMA_GATHER") ? 0 : 1;
     if (tile_mask && use_tma && u2_conv_fwd_tma_supported(Cs, Cd, K))
         return u2_conv_fwd_tma(X, n_src, Cs, W, w_transposed, tableP, perm, tile_mask, ld, n_dst, K, Cd, Y, scratch,
@@ -128,9 +128,31 @@ extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const
         return u2_conv_fwd_mt(X, n_src, Cs, W, w_transposed, tableP, perm, tile_mask, ld, n_dst, K, Cd, Y, scratch,
                               scratch_bytes, (cudaStream_t)stream);
     return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
-                          (cudaStream_t)stream);
+                          nullptr, (cudaStream_t)stream);
 #else
     u2_set_error("u2_conv_fwd_perm: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+// Conv forward that also leaves the per-warp column sums of Y behind (fused BatchNorm statistics):
+// tile_stats fp32 [4 * ceil(rows / 128)][2][Cd], rows = ld with a row permutation, n_dst without.
+extern "C" size_t u2_conv_tile_stats_parts(int64_t rows) { return (size_t)(4 * ((rows + 127) / 128)); }
+
+extern "C" int u2_conv_fwd_stats(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
+                                 const int32_t *table, const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd,
+                                 float *Y, int32_t math, void *scratch, size_t scratch_bytes, float *tile_stats,
+                                 size_t tile_stats_bytes, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    if (check_common(X, W, table, Y, Cs, Cd, K, ld, n_dst, "u2_conv_fwd_stats")) return 1;
+    U2_CHECK_ARG((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math),
+                 "u2_conv_fwd_stats: unsupported shape/math");
+    U2_CHECK_ARG(tile_stats && tile_stats_bytes >= u2_conv_tile_stats_parts(perm ? ld : n_dst) * 2 * Cd * sizeof(float),
+                 "u2_conv_fwd_stats: tile_stats too small");
+    return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
+                          tile_stats, (cudaStream_t)stream);
+#else
+    u2_set_error("u2_conv_fwd_stats: built without the tcgen05 path");
     return 1;
 #endif
 }

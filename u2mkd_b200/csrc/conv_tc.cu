@@ -161,7 +161,38 @@ struct FwdParams {
     int Cs, Cd, K, NT, stages, tmem_cols;
     long long *dbg;  // optional per-CTA phase timestamps (U2_DEBUG_CONV_TIMING)
     int cp_mode;
+    float *tile_stats;  // optional [tiles * 4][2][Cd]: per-warp column sums / sums of squares of Y (fused BatchNorm)
 };
+
+// Column sums over the 32 rows a warp holds (lane = row, r[j] = column j): a transposing butterfly, 31 shuffles
+// instead of 32 x 5; on return lane l holds the sum of column l.
+__device__ __forceinline__ float warp_colsum32(float (&r)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; i++) {
+            const float send = up ? r[i] : r[i + o];
+            const float keep = up ? r[i + o] : r[i];
+            r[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, o);
+        }
+    }
+    return r[0];
+}
+
+// columns [c, c + 32) of this warp's 32 accumulator rows -> tile_stats (sum, then sum of squares)
+__device__ __forceinline__ void stats32(const uint32_t (&a)[16], const uint32_t (&b)[16], int lane, float *ts, int Cd) {
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { r[i] = __uint_as_float(a[i]); r[16 + i] = __uint_as_float(b[i]); }
+    ts[lane] = warp_colsum32(r, lane);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        r[i] = __uint_as_float(a[i]) * __uint_as_float(a[i]);
+        r[16 + i] = __uint_as_float(b[i]) * __uint_as_float(b[i]);
+    }
+    ts[Cd + lane] = warp_colsum32(r, lane);
+}
 
 // ROWB = bytes of one gathered row per pipeline stage (128 or 64): 32/16 fp32 or 64/32 bf16 channels.
 template <int ROWB, bool BF16>
@@ -281,6 +312,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             if (dbg && tid == 0) dbg[3] = clock64();
             // 64 accumulator columns per round: four tcgen05.ld in flight, one wait
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+            // rows without a destination (padding of the sorted table) have no neighbours: their accumulators are 0
+            float *ts = p.tile_stats ? p.tile_stats + ((size_t)blockIdx.x * 4 + warp) * 2 * p.Cd + nt * NT : nullptr;
             int c0 = 0;
             for (; c0 + 64 <= NT; c0 += 64) {
                 uint32_t v0[16], v1[16], v2[16], v3[16];
@@ -298,8 +331,27 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                         *reinterpret_cast<uint4 *>(yrow + c0 + 48 + j) = make_uint4(v3[j], v3[j + 1], v3[j + 2], v3[j + 3]);
                     }
                 }
+                if (ts) {
+                    stats32(v0, v1, lane, ts + c0, p.Cd);
+                    stats32(v2, v3, lane, ts + c0 + 32, p.Cd);
+                }
             }
-            for (; c0 < NT; c0 += 16) {
+            if (c0 + 32 <= NT) {
+                uint32_t v0[16], v1[16];
+                tmem_ld16(t_row + (uint32_t)c0, v0);
+                tmem_ld16(t_row + (uint32_t)c0 + 16, v1);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                        *reinterpret_cast<uint4 *>(yrow + c0 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+                    }
+                }
+                if (ts) stats32(v0, v1, lane, ts + c0, p.Cd);
+                c0 += 32;
+            }
+            for (; c0 < NT; c0 += 16) {  // NT % 32 == 16: the launcher refuses tile_stats for such shapes
                 uint32_t v[16];
                 tmem_ld16(t_row + (uint32_t)c0, v);
                 tmem_ld_wait();
@@ -309,8 +361,13 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                         *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             }
-        } else if (live) {
-            for (int c0 = 0; c0 < NT; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            if (live)
+                for (int c0 = 0; c0 < NT; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
+            if (p.tile_stats) {
+                float *ts = p.tile_stats + ((size_t)blockIdx.x * 4 + warp) * 2 * p.Cd + nt * NT;
+                for (int c = lane; c < NT; c += 32) { ts[c] = 0.f; ts[p.Cd + c] = 0.f; }
+            }
         }
     } else if (warp == 4) {
         // ============================ B producer ============================
@@ -1118,9 +1175,10 @@ static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_
 // X: fp32 rows (math TF32) or bf16 rows (math BF16); W always the fp32 parameter tensor.
 int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
-                   void *scratch, size_t scratch_bytes, cudaStream_t st) {
+                   void *scratch, size_t scratch_bytes, float *tile_stats, cudaStream_t st) {
     const bool bf16 = math == U2_MATH_BF16;
     const int es = bf16 ? 2 : 4;
+    U2_CHECK_ARG(!tile_stats || pick_nt(Cd) % 32 == 0, "u2_conv_fwd_tc: fused column statistics need Cd tiles of 32 (Cd=%d)", Cd);
     U2_CHECK_ARG(n_src * (int64_t)Cs * es < 0xFFFFFFFFLL, "u2_conv_fwd_tc: source tensor too large for 32-bit byte offsets");
     if (n_dst == 0) return 0;
     const int ROWB = pick_rowb(Cs, es), NT = pick_nt(Cd);
@@ -1148,6 +1206,7 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     FwdParams p;
     p.X = (const uint8_t *)X; p.Wt = (const uint8_t *)scratch; p.table = table; p.perm = perm; p.Y = Y;
     p.dbg = nullptr;
+    p.tile_stats = tile_stats;
     static const int cp_mode = getenv("U2_CPASYNC_MODE") ? atoi(getenv("U2_CPASYNC_MODE")) : 1;  // .ca measured 15-25 % faster
     p.cp_mode = cp_mode;
     p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;

@@ -94,12 +94,20 @@ __global__ void bn_finalize_kernel(const double *__restrict__ sums, int C, float
 
 __device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
+// round-to-nearest-even, same packing as cast_bf16_kernel (conv_tc.cu): low half = first element
+__device__ __forceinline__ uint2 bf16x4(const float4 v) {
+    uint2 o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
+    return o;
+}
+
 // y = x * scale + shift (+ReLU); scale = invstd * gamma, shift = beta - mean * scale: computed once per thread
 template <bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict__ x, int64_t n, int tx, int ty,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                       float4 *__restrict__ y) {
+                                                       float4 *__restrict__ y, uint2 *__restrict__ yb) {
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
     const int c = cx * 4;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
@@ -112,14 +120,18 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict_
         if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         return o;
     };
+    auto put = [&](int64_t i, float4 o) {
+        y[i] = o;
+        if (yb) yb[i] = bf16x4(o);  // the next conv's bf16 operand, written while the row is in registers
+    };
     int64_t r = r0 + ry;
     for (; r + 3 * ty < r1; r += 4 * ty) {
         const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
         const float4 v2 = __ldg(x + (r + 2 * ty) * tx + cx), v3 = __ldg(x + (r + 3 * ty) * tx + cx);
-        y[r * tx + cx] = f(v0); y[(r + ty) * tx + cx] = f(v1);
-        y[(r + 2 * ty) * tx + cx] = f(v2); y[(r + 3 * ty) * tx + cx] = f(v3);
+        put(r * tx + cx, f(v0)); put((r + ty) * tx + cx, f(v1));
+        put((r + 2 * ty) * tx + cx, f(v2)); put((r + 3 * ty) * tx + cx, f(v3));
     }
-    for (; r < r1; r += ty) y[r * tx + cx] = f(__ldg(x + r * tx + cx));
+    for (; r < r1; r += ty) put(r * tx + cx, f(__ldg(x + r * tx + cx)));
 }
 
 // dsum[c] += sum dz ; dsum[C + c] += sum dz * xhat     (dz = dy masked by the recomputed ReLU)
@@ -163,7 +175,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4 *__restr
                                                            int64_t n, int tx, int ty, const float *__restrict__ mean,
                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                            const float *__restrict__ beta, const double *__restrict__ dsum,
-                                                           const double *__restrict__ count, float4 *__restrict__ dx) {
+                                                           const double *__restrict__ count, float4 *__restrict__ dx,
+                                                           uint2 *__restrict__ dxb) {
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
     const int C = tx * 4, c = cx * 4;
     const double inv_count = *count > 0.0 ? 1.0 / *count : 0.0;
@@ -186,14 +199,41 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4 *__restr
         return make_float4(gi.x * (d.x - a.x - h.x * bb.x), gi.y * (d.y - a.y - h.y * bb.y), gi.z * (d.z - a.z - h.z * bb.z),
                            gi.w * (d.w - a.w - h.w * bb.w));
     };
+    auto put = [&](int64_t i, float4 o) {
+        if (dx) dx[i] = o;
+        if (dxb) dxb[i] = bf16x4(o);  // the conv backward's bf16 operand (fused conv+BN: the only output)
+    };
     int64_t r = r0 + ry;
     for (; r + ty < r1; r += 2 * ty) {
         const float4 v0 = __ldg(x + r * tx + cx), v1 = __ldg(x + (r + ty) * tx + cx);
         const float4 d0 = __ldg(dy + r * tx + cx), d1 = __ldg(dy + (r + ty) * tx + cx);
-        dx[r * tx + cx] = f(v0, d0);
-        dx[(r + ty) * tx + cx] = f(v1, d1);
+        put(r * tx + cx, f(v0, d0));
+        put((r + ty) * tx + cx, f(v1, d1));
     }
-    for (; r < r1; r += ty) dx[r * tx + cx] = f(__ldg(x + r * tx + cx), __ldg(dy + r * tx + cx));
+    for (; r < r1; r += ty) put(r * tx + cx, f(__ldg(x + r * tx + cx), __ldg(dy + r * tx + cx)));
+}
+
+// sums[c] += sum_p part[p][0][c], sums[C + c] += sum_p part[p][1][c]: the per-warp column sums the conv
+// epilogue left behind (conv_tc.cu), so that BatchNorm needs no statistics pass over the conv output
+__global__ void __launch_bounds__(256) bn_tiles_reduce_kernel(const float *__restrict__ part, int64_t P, int C,
+                                                              double *__restrict__ sums) {
+    __shared__ double s_red[2][8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    double s = 0.0, q = 0.0;
+    if (col < C)
+        for (int64_t p = (int64_t)blockIdx.y * 8 + ry; p < P; p += (int64_t)gridDim.y * 8) {
+            s += (double)__ldg(part + (2 * p) * C + col);
+            q += (double)__ldg(part + (2 * p + 1) * C + col);
+        }
+    s_red[0][ry][cx] = s;
+    s_red[1][ry][cx] = q;
+    __syncthreads();
+    if (ry == 0 && col < C) {
+        for (int j = 1; j < 8; j++) { s += s_red[0][j][cx]; q += s_red[1][j][cx]; }
+        atomicAdd(sums + col, s);
+        atomicAdd(sums + C + col, q);
+    }
 }
 
 }  // namespace
@@ -217,13 +257,29 @@ extern "C" int u2_bn_stats(const float *x, int64_t n, int32_t C, double *sums, u
     return 0;
 }
 
-extern "C" int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
-                           const float *gamma, const float *beta, int32_t relu, float *y, float *save_mean,
-                           float *save_invstd, float *running_mean, float *running_var, u2_stream_t stream) {
+extern "C" int u2_bn_stats_from_tiles(const float *tile_stats, int64_t n_parts, int32_t C, int64_t n, double *sums,
+                                      u2_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    U2_CHECK_ARG(tile_stats && sums && C > 0 && n_parts >= 0, "u2_bn_stats_from_tiles: bad arguments");
+    U2_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)(2 * C) * sizeof(double), st));
+    const double cnt = (double)n;
+    U2_CUDA_OK(cudaMemcpyAsync(sums + 2 * C, &cnt, sizeof(double), cudaMemcpyHostToDevice, st));
+    if (n_parts == 0) return 0;
+    int64_t chunks = u2_ceil_div(n_parts, 64);
+    if (chunks > 64) chunks = 64;
+    bn_tiles_reduce_kernel<<<dim3((unsigned)((C + 31) / 32), (unsigned)chunks), 256, 0, st>>>(tile_stats, n_parts, C, sums);
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
+                                const float *gamma, const float *beta, int32_t relu, float *y, void *y_bf16,
+                                float *save_mean, float *save_invstd, float *running_mean, float *running_var,
+                                u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(u2_bn_supported(C), "u2_bn_apply: C=%d", C);
     U2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)save_mean |
-                   (uintptr_t)save_invstd) & 15) == 0, "u2_bn_apply: pointers must be 16-byte aligned");
+                   (uintptr_t)save_invstd | (uintptr_t)y_bf16) & 15) == 0, "u2_bn_apply: pointers must be 16-byte aligned");
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, eps, momentum, save_mean, save_invstd, running_mean,
                                                          running_var);
     U2_LAUNCH_OK();
@@ -231,11 +287,18 @@ extern "C" int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *s
     const BnGeom g = bn_geom(C);
     const unsigned grid = (unsigned)u2_ceil_div(n, BN_ROWS_PER_BLOCK);
     if (relu)
-        bn_apply_kernel<true><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y);
+        bn_apply_kernel<true><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y, (uint2 *)y_bf16);
     else
-        bn_apply_kernel<false><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y);
+        bn_apply_kernel<false><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y, (uint2 *)y_bf16);
     U2_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
+                           const float *gamma, const float *beta, int32_t relu, float *y, float *save_mean,
+                           float *save_invstd, float *running_mean, float *running_var, u2_stream_t stream) {
+    return u2_bn_apply_dual(x, n, C, sums, eps, momentum, gamma, beta, relu, y, nullptr, save_mean, save_invstd, running_mean,
+                            running_var, stream);
 }
 
 // dsum: fp64 [2C], zeroed by the call: dsum[c] = sum dz (= grad beta), dsum[C+c] = sum dz*xhat (= grad gamma)
@@ -263,20 +326,28 @@ extern "C" int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int3
     return 0;
 }
 
-extern "C" int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
-                               const float *gamma, const float *beta, const double *dsum, const double *count_dev,
-                               int32_t relu, float *dx, u2_stream_t stream) {
+extern "C" int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, const float *mean,
+                                    const float *invstd, const float *gamma, const float *beta, const double *dsum,
+                                    const double *count_dev, int32_t relu, float *dx, void *dx_bf16, u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(u2_bn_supported(C), "u2_bn_bwd_apply: C=%d", C);
+    U2_CHECK_ARG(dx || dx_bf16, "u2_bn_bwd_apply: no output");
+    U2_CHECK_ARG((((uintptr_t)dx | (uintptr_t)dx_bf16) & 15) == 0, "u2_bn_bwd_apply: outputs must be 16-byte aligned");
     if (n == 0) return 0;
     const BnGeom g = bn_geom(C);
     const unsigned grid = (unsigned)u2_ceil_div(n, BN_ROWS_PER_BLOCK);
     if (relu)
         bn_bwd_apply_kernel<true><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd,
-                                                                 gamma, beta, dsum, count_dev, (float4 *)dx);
+                                                                 gamma, beta, dsum, count_dev, (float4 *)dx, (uint2 *)dx_bf16);
     else
         bn_bwd_apply_kernel<false><<<grid, g.tx * g.ty, 0, st>>>((const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd,
-                                                                  gamma, beta, dsum, count_dev, (float4 *)dx);
+                                                                  gamma, beta, dsum, count_dev, (float4 *)dx, (uint2 *)dx_bf16);
     U2_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
+                               const float *gamma, const float *beta, const double *dsum, const double *count_dev,
+                               int32_t relu, float *dx, u2_stream_t stream) {
+    return u2_bn_bwd_apply_dual(dy, x, n, C, mean, invstd, gamma, beta, dsum, count_dev, relu, dx, nullptr, stream);
 }

@@ -433,7 +433,7 @@ class ConvolutionFn(Function):
             table, n_dst = kmap.nbrT, kmap.n_in
             assert feats.shape[0] == kmap.n_out, (feats.shape, kmap.sizes)
         m_fwd = _layer_math(math, cin, cout, K)
-        x_op = cast_bf16(feats) if m_fwd == MATH_BF16 else feats
+        x_op = bf16_view(feats) if m_fwd == MATH_BF16 else feats
         out = _conv_gather_gemm("fwd", kmap, x_op, weight, False, table, n_dst, cout, m_fwd, side=bool(transposed))
         # the bf16 copy (half the bytes) is what wgrad needs later; otherwise keep the fp32 rows
         ctx.save_for_backward(x_op, weight)
@@ -528,6 +528,143 @@ class BatchNormFn(Function):
                                     _st()))
         _count(2)
         return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------ conv -> BatchNorm(+ReLU), one autograd node
+def stash_bf16(x: torch.Tensor, xb: torch.Tensor) -> None:
+    """Remember the bf16 copy a kernel produced together with `x`; `bf16_view` hands it to the next conv
+    as long as `x` has not been modified in place since."""
+    x._u2_bf16 = (xb, x._version)
+
+
+def bf16_view(x: torch.Tensor) -> torch.Tensor:
+    st = getattr(x, "_u2_bf16", None)
+    if st is not None and st[1] == x._version and st[0].shape == x.shape:
+        return st[0]
+    return cast_bf16(x)
+
+
+class ConvBNReLUFn(Function):
+    """Sequential(Conv3d, BatchNorm[, ReLU]) of core/models/build_blocks.py:21-84 as one node (bf16 math):
+    forward : conv (epilogue leaves the column sums of Y) -> [all-reduce] -> normalise(+ReLU), fp32 + bf16 out
+    backward: BN reduce -> [all-reduce] -> BN dx written as bf16 only -> dgrad + wgrad
+    i.e. no statistics pass over Y, no cast pass before the next conv or before dgrad/wgrad, and the fp32
+    gradient of Y never exists."""
+
+    @staticmethod
+    def forward(ctx, feats, feats_bf16, weight, gamma, beta, running_mean, running_var, momentum, eps, relu, group,
+                kmap: KernelMap, transposed: bool):
+        K, cin, cout = weight.shape
+        weight = weight.contiguous()
+        if not transposed:
+            table, n_dst, side = kmap.nbr, kmap.n_out, False
+        else:
+            table, n_dst, side = kmap.nbrT, kmap.n_in, True
+        dev = feats_bf16.device
+        n_src = feats_bf16.shape[0]
+        ld = table.shape[1]
+        y = torch.empty((n_dst, cout), dtype=torch.float32, device=dev)
+        sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, MATH_BF16)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        if _state["sort_tiles"]:
+            tab, perm, _ = kmap.sorted_tables(side)
+            rows = ld
+        else:
+            tab, perm, rows = table, None, n_dst
+        parts = lib().u2_conv_tile_stats_parts(rows)
+        tstats = torch.empty((parts, 2, cout), dtype=torch.float32, device=dev)
+        _timed("fwd", kmap, n_dst, K, cin, cout, lambda: check(lib().u2_conv_fwd_stats(
+            feats_bf16.data_ptr(), n_src, cin, weight.data_ptr(), 0, tab.data_ptr(), _ptr(perm), ld, n_dst, K, cout,
+            y.data_ptr(), MATH_BF16, scratch.data_ptr(), sbytes, tstats.data_ptr(), tstats.numel() * 4, _st())))
+        sums = torch.empty(2 * cout + 1, dtype=torch.float64, device=dev)
+        check(lib().u2_bn_stats_from_tiles(tstats.data_ptr(), parts, cout, n_dst, sums.data_ptr(), _st()))
+        if group is not None:
+            torch.distributed.all_reduce(sums, group=group)
+        z = torch.empty_like(y)
+        zb = torch.empty((n_dst, cout), dtype=torch.bfloat16, device=dev)
+        mean = torch.empty(cout, dtype=torch.float32, device=dev)
+        invstd = torch.empty(cout, dtype=torch.float32, device=dev)
+        check(lib().u2_bn_apply_dual(y.data_ptr(), n_dst, cout, sums.data_ptr(), float(eps), float(momentum),
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), z.data_ptr(), zb.data_ptr(),
+                                     mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _st()))
+        _count(5)
+        ctx.save_for_backward(feats_bf16, weight, y, gamma, beta, mean, invstd, sums)
+        ctx.misc = (kmap, transposed, relu, group)
+        ctx.mark_non_differentiable(zb)
+        ctx.set_materialize_grads(False)  # no zero-filled "gradient" for the bf16 copy
+        return z, zb
+
+    @staticmethod
+    def backward(ctx, dz, _dzb):
+        xb, weight, y, gamma, beta, mean, invstd, sums = ctx.saved_tensors
+        kmap, transposed, relu, group = ctx.misc
+        if dz is None:
+            return (None,) * 13
+        dz = dz.contiguous().float()
+        K, cin, cout = weight.shape
+        n, c = y.shape
+        dev = y.device
+        dsum = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        check(lib().u2_bn_bwd_reduce(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), _st()))
+        dbeta, dgamma = dsum[:c].float(), dsum[c:].float()
+        if group is not None:
+            dsum = dsum.clone()
+            torch.distributed.all_reduce(dsum, group=group)
+        dyb = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+        check(lib().u2_bn_bwd_apply_dual(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
+                                         gamma.data_ptr(), beta.data_ptr(), dsum.data_ptr(), sums.data_ptr() + 16 * c,
+                                         int(relu), None, dyb.data_ptr(), _st()))
+        _count(3)
+        grad_feats = grad_weight = None
+        if ctx.needs_input_grad[0]:
+            bwd_table = kmap.nbr if transposed else kmap.nbrT
+            grad_feats = _conv_gather_gemm("dgrad", kmap, dyb, weight, True, bwd_table, xb.shape[0], cin, MATH_BF16,
+                                           side=not transposed)
+        if ctx.needs_input_grad[2]:
+            grad_weight = torch.empty_like(weight)
+            flat = kmap.flat_pairs
+            _timed("wgrad", kmap, n, K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                xb.data_ptr(), cin, dyb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
+                flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, _st())))
+        return (grad_feats, None, grad_weight, dgamma, dbeta) + (None,) * 8
+
+
+def _bn_group(bn):
+    """Process group whose ranks share the statistics (SyncBatchNorm in training), else None."""
+    import torch.distributed as dist
+    if isinstance(bn, torch.nn.SyncBatchNorm) and bn.training and dist.is_available() and dist.is_initialized():
+        pg = bn.process_group if bn.process_group is not None else dist.group.WORLD
+        if dist.get_world_size(pg) > 1:
+            return pg
+    return None
+
+
+def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, relu: bool):
+    """conv3d -> bn(+relu) on feature matrices. Fused node where the bf16 tcgen05 kernels cover the layer,
+    otherwise the two separate operators (same results up to summation order)."""
+    group = _bn_group(bn)
+    K, cin, cout = weight.shape
+    n_dst = kmap.n_in if transposed else kmap.n_out
+    fused = (_state["math"] == MATH_BF16 and _state.get("fuse_conv_bn", True) and bn.training and bn.affine
+             and feats.is_cuda and feats.dtype == torch.float32 and weight.dtype == torch.float32 and n_dst > 1
+             and feats.shape[0] > 0 and cout % 32 == 0 and lib().u2_bn_supported(cout)
+             and lib().u2_conv_tc_shape_supported(cin, cout, K, MATH_BF16)
+             and lib().u2_conv_tc_shape_supported(cout, cin, K, MATH_BF16)
+             and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, MATH_BF16)
+             and (cout // ((cout + 255) // 256)) % 32 == 0)
+    if not fused:
+        return batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, relu, group)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    feats = feats.contiguous()
+    z, zb = ConvBNReLUFn.apply(feats, bf16_view(feats), weight, bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu,
+                               group, kmap, transposed)
+    stash_bf16(z, zb)
+    return z
 
 
 def batch_norm_relu(x, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = False, group=None):

@@ -35,9 +35,11 @@ def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1)
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, stride=1, dilation=1,
-           transposed: bool = False) -> SparseTensor:
+           transposed: bool = False, epilogue=None) -> SparseTensor:
     """F.conv3d of torchsparse v1.4.0: kernel-map lookup/build, then
-    one fused gather-GEMM kernel (ops.ConvolutionFn) instead of K gather/mm/scatter rounds."""
+    one fused gather-GEMM kernel (ops.ConvolutionFn) instead of K gather/mm/scatter rounds.
+    `epilogue=(bn_module, relu)` (set by u2mkd_b200.fusion.optimize, not part of the torchsparse signature)
+    applies that BatchNorm(+ReLU) to the result inside the same autograd node."""
     feats, coords = input.feats, input.coords
     kernel_size, stride, dilation = (make_ntuple(v, ndim=3) for v in (kernel_size, stride, dilation))
     unit = (1, 1, 1)
@@ -56,14 +58,24 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
             input.kmaps[key] = kmap
         elif any(s > 1 for s in stride):
             coords = input.cmaps[out_stride]  # upstream skips this on a cache hit
-        feats = ops.sparse_conv(feats, weight, kmap, transposed=False)
+        if epilogue is not None and bias is None:
+            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, False, *epilogue)
+            epilogue = None
+        else:
+            feats = ops.sparse_conv(feats, weight, kmap, transposed=False)
     else:
         out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
         kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
-        feats = ops.sparse_conv(feats, weight, kmap, transposed=True)
+        if epilogue is not None and bias is None:
+            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, True, *epilogue)
+            epilogue = None
+        else:
+            feats = ops.sparse_conv(feats, weight, kmap, transposed=True)
         coords = input.cmaps[out_stride]
     if bias is not None:
         feats = feats + bias
+    if epilogue is not None:  # 1x1x1 kernels and biased convs: the separate BatchNorm kernels
+        feats = ops.batch_norm_relu(feats, epilogue[0], epilogue[1], ops._bn_group(epilogue[0]))
     output = SparseTensor(coords=coords, feats=feats, stride=out_stride)
     output.cmaps = input.cmaps
     output.cmaps.setdefault(output.stride, output.coords)

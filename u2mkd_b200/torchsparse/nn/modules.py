@@ -57,7 +57,7 @@ class Conv3d(nn.Module):
 
     def forward(self, input: SparseTensor) -> SparseTensor:
         return F.conv3d(input, self.kernel, kernel_size=self.kernel_size, bias=self.bias, stride=self.stride,
-                        dilation=self.dilation, transposed=self.transposed)
+                        dilation=self.dilation, transposed=self.transposed, epilogue=getattr(self, "_u2_epilogue", None))
 
 
 class BatchNorm(nn.BatchNorm1d):
