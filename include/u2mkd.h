@@ -178,12 +178,17 @@ int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, 
  * u2_bn_apply derives mean / invstd (written to save_mean / save_invstd, running stats updated if non-NULL).
  * backward: dsum fp64 [2C] = (sum dz, sum dz*xhat) = (grad beta, grad gamma); all-reduce a copy for dx.    */
 int u2_bn_supported(int32_t C);
-int u2_bn_stats(const float *x, int64_t n, int32_t C, double *sums, u2_stream_t stream);
+/* the two reductions leave one fp32 row of partial sums per CTA in `scratch` (u2_bn_scratch_bytes(C), 16-byte aligned)
+ * and fold them in a second small kernel: no same-address atomics from every CTA */
+size_t u2_bn_scratch_bytes(int32_t C);
+int u2_bn_stats(const float *x, int64_t n, int32_t C, double *sums, void *scratch, size_t scratch_bytes,
+                u2_stream_t stream);
 int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
                 const float *gamma, const float *beta, int32_t relu, float *y, float *save_mean, float *save_invstd,
                 float *running_mean, float *running_var, u2_stream_t stream);
 int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
-                     const float *gamma, const float *beta, int32_t relu, double *dsum, u2_stream_t stream);
+                     const float *gamma, const float *beta, int32_t relu, double *dsum, void *scratch,
+                     size_t scratch_bytes, u2_stream_t stream);
 int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
                     const float *gamma, const float *beta, const double *dsum, const double *count_dev, int32_t relu,
                     float *dx, u2_stream_t stream);

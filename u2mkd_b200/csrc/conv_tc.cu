@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(256) pretile_weights_kernel(const float *__res
 // the pair list is the kernel map's compacted list (ascending k, then output row), so no MMA
 // cycle and no gathered byte is spent on missing neighbours.  Partial tiles are combined with
 // 16-byte fp32 reductions into dW (zeroed by the caller).
-constexpr int WG_PAIRS = 4096;  // pairs per CTA
+constexpr int WG_PAIRS = 4096;  // most pairs per CTA (the launcher takes fewer for small maps, see u2_conv_wgrad_tc)
 
 __host__ __device__ constexpr uint32_t make_idesc_mn(bool bf16, int M, int N) {
     return (bf16 ? make_idesc_bf16(M, N) : make_idesc_tf32(M, N)) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
@@ -947,6 +947,7 @@ struct WgradParams {
     float *dW;
     int64_t ld;
     int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt, cp_mode, TM;
+    int wg_pairs;  // pairs per CTA, multiple of 128, <= WG_PAIRS
 };
 
 template <bool BF16>
@@ -960,7 +961,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     const int A_BYTES = TM * G::A_BYTES;
     const int stage_bytes = A_BYTES + B_BYTES;
     int2 *s_pairs = reinterpret_cast<int2 *>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_pairs + WG_PAIRS);
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_pairs + p.wg_pairs);
     uint64_t *s_empty = s_full + MAX_STAGES;
     uint64_t *s_accum = s_empty + MAX_STAGES;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_accum + 1);
@@ -972,9 +973,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     int koff = 0;
     for (int j = 0; j < k; j++) koff += __ldg(p.nbsizes + j);
     const int n_k = __ldg(p.nbsizes + k);
-    const int c0 = blockIdx.x * WG_PAIRS;
+    const int c0 = blockIdx.x * p.wg_pairs;
     if (c0 >= n_k) return;
-    const int n_pairs = min(WG_PAIRS, n_k - c0);
+    const int n_pairs = min(p.wg_pairs, n_k - c0);
     const int n_items = (n_pairs + G::KR - 1) / G::KR;
 
     if (tid == 0) {
@@ -1264,7 +1265,24 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     p.n_mt = (Cs + TILE_M - 1) / TILE_M;
     p.n_nt = Cd / NT;
     const int cpa = bf16 ? 64 : 32, atom = bf16 ? 8192 : 4096;
-    const size_t fixed = (size_t)WG_PAIRS * sizeof(int2) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
+    // Pairs per CTA.  A CTA walks its pairs serially (64 per stage), so a small map cut into 4096-pair chunks leaves
+    // most SMs idle behind a few long chains (measured: every layer below ~100k rows took the same 0.16 ms).  Aim
+    // at `target` working CTAs, assuming ~40 % of the K * n_rows table entries are present; the price of smaller
+    // chunks is one more fp32 reduction of the Cs x Cd tile into dW per chunk, hence the floor.
+    static const int wg_fixed = getenv("U2_WGRAD_PAIRS") ? atoi(getenv("U2_WGRAD_PAIRS")) : 0;
+    static const int wg_min = getenv("U2_WGRAD_PAIRS_MIN") ? atoi(getenv("U2_WGRAD_PAIRS_MIN")) : 1024;
+    static const int wg_target = getenv("U2_WGRAD_TARGET_CTAS") ? atoi(getenv("U2_WGRAD_TARGET_CTAS")) : 8 * U2_NUM_SMS;
+    {
+        const int tm0 = (p.n_mt < 4 ? p.n_mt : 4);
+        const int64_t slices = (int64_t)u2_ceil_div(p.n_mt, tm0) * p.n_nt;
+        int64_t want = (int64_t)(0.4 * (double)n_rows * K) * slices / wg_target;
+        want = (want + 127) / 128 * 128;
+        if (want < wg_min) want = wg_min;
+        if (want > WG_PAIRS) want = WG_PAIRS;
+        if (wg_fixed > 0) want = wg_fixed;
+        p.wg_pairs = (int)want;
+    }
+    const size_t fixed = (size_t)p.wg_pairs * sizeof(int2) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
     const size_t budget = 227 * 1024;
     // input slices per CTA: every slice re-gathers the dY rows, so take as many as TMEM (512 columns)
     // and shared memory (>= 3 stages) allow
@@ -1290,7 +1308,7 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     p.stages = stages;
     const size_t smem = stages * stage_bytes + fixed;
     // a single offset has at most n_rows pairs (one per row of the table's row side)
-    dim3 grid((unsigned)u2_ceil_div(n_rows, WG_PAIRS), (unsigned)K, (unsigned)(u2_ceil_div(p.n_mt, TM) * p.n_nt));
+    dim3 grid((unsigned)u2_ceil_div(n_rows, p.wg_pairs), (unsigned)K, (unsigned)(u2_ceil_div(p.n_mt, TM) * p.n_nt));
     if (bf16) {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_wgrad_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);

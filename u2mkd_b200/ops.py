@@ -483,6 +483,11 @@ def sparse_conv(feats, weight, kmap: KernelMap, transposed: bool = False, math: 
 
 
 # -------------------------------------------------------------------------------- batch norm (+ReLU)
+def _bn_scratch(c: int, device) -> torch.Tensor:
+    """Per-CTA partial sums of the two BatchNorm reductions (stream-ordered allocation from torch's pool)."""
+    return torch.empty(lib().u2_bn_scratch_bytes(c), dtype=torch.uint8, device=device)
+
+
 class BatchNormFn(Function):
     """Training-mode BatchNorm over [n, C] features with an optional fused ReLU and an optional
     process group (SyncBatchNorm semantics: statistics over the rows of all ranks)."""
@@ -494,7 +499,8 @@ class BatchNormFn(Function):
         n, c = x.shape
         st = _st()
         sums = torch.empty(2 * c + 1, dtype=torch.float64, device=x.device)
-        check(lib().u2_bn_stats(x.data_ptr(), n, c, sums.data_ptr(), st))
+        scratch = _bn_scratch(c, x.device)
+        check(lib().u2_bn_stats(x.data_ptr(), n, c, sums.data_ptr(), scratch.data_ptr(), scratch.numel(), st))
         if group is not None:
             torch.distributed.all_reduce(sums, group=group)
         y = torch.empty_like(x)
@@ -516,8 +522,10 @@ class BatchNormFn(Function):
         n, c = x.shape
         st = _st()
         dsum = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        scratch = _bn_scratch(c, x.device)
         check(lib().u2_bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), st))
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), scratch.data_ptr(),
+                                     scratch.numel(), st))
         dbeta, dgamma = dsum[:c].float(), dsum[c:].float()   # local sums: DDP averages parameter grads
         if group is not None:
             dsum = dsum.clone()
@@ -605,8 +613,10 @@ class ConvBNReLUFn(Function):
         n, c = y.shape
         dev = y.device
         dsum = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        scratch = _bn_scratch(c, dev)
         check(lib().u2_bn_bwd_reduce(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), _st()))
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), scratch.data_ptr(),
+                                     scratch.numel(), _st()))
         dbeta, dgamma = dsum[:c].float(), dsum[c:].float()
         if group is not None:
             dsum = dsum.clone()
