@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size")
     ap.add_argument("--no-fusion", action="store_true", help="keep torch BatchNorm/ReLU modules unfused")
+    ap.add_argument("--no-fused-sgd", action="store_true", help="torch's default (foreach) SGD instead of fused=True")
+    ap.add_argument("--no-residual-fusion", action="store_true", help="ResidualBlock tail as separate add / ReLU passes")
     ap.add_argument("--no-conv-bn", action="store_true", help="BatchNorm as its own node after each conv (A/B of the conv+BN fusion)")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu launch lists): no allocator pre-pass, no e2e region, no CPU baseline")
@@ -263,11 +265,13 @@ def run_ours(args, w):
         net = fam.SparseSyncBatchNorm.convert_sync_batchnorm(net)  # train_spformer.py:79
     if not args.no_fusion:
         from u2mkd_b200 import fusion
-        fusion.optimize(net, fuse_conv_bn=not args.no_conv_bn)  # same module tree / parameters; BN(+ReLU) run the fused kernels
+        fusion.optimize(net, fuse_conv_bn=not args.no_conv_bn, fuse_residual=not args.no_residual_fusion)  # same module tree / parameters; BN(+ReLU) run the fused kernels
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.bucket_mb)  # train_spformer.py:82-83
-    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    # torch's single-pass multi-tensor SGD (same update rule as train_spformer.py's optimizer, one kernel per chunk)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4,
+                          fused=not args.no_fused_sgd)
 
     pool = make_pool(args, w, rank, args.pool)
     n_params = sum(p.numel() for p in net.parameters())
@@ -382,6 +386,8 @@ def run_ours(args, w):
                            "parallelism": f"dp{world}" + ("" if world == 1 or args.no_sync_bn else "+syncbn"),
                            "fused_bn_relu": not args.no_fusion,
                            "fused_conv_bn": not (args.no_fusion or args.no_conv_bn),
+                           "fused_residual": not (args.no_fusion or args.no_conv_bn or args.no_residual_fusion),
+                           "optimizer_impl": "torch fused" if not args.no_fused_sgd else "torch foreach",
                            "l2": "activations (>1 GB/step) exceed the 126 MB L2; a different scan batch every step"},
                 "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},

@@ -187,8 +187,8 @@ int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *sums, float 
                 const float *gamma, const float *beta, int32_t relu, float *y, float *save_mean, float *save_invstd,
                 float *running_mean, float *running_var, u2_stream_t stream);
 int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
-                     const float *gamma, const float *beta, int32_t relu, double *dsum, void *scratch,
-                     size_t scratch_bytes, u2_stream_t stream);
+                     const float *gamma, const float *beta, int32_t relu, const float *out_mask, double *dsum,
+                     void *scratch, size_t scratch_bytes, u2_stream_t stream);
 int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
                     const float *gamma, const float *beta, const double *dsum, const double *count_dev, int32_t relu,
                     float *dx, u2_stream_t stream);
@@ -199,7 +199,10 @@ int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const
  * tile_stats fp32 [u2_conv_tile_stats_parts(rows)][2][Cd], rows = ld with perm, n_dst without; needs Cd tiles % 32 == 0.
  * u2_bn_stats_from_tiles folds them into the fp64 [2C+1] sums buffer of u2_bn_apply (no pass over Y).
  * The *_dual variants also emit the bf16 copy the next conv (forward) / the conv backward consumes, so that
- * no separate u2_cast_bf16 pass is needed; in u2_bn_bwd_apply_dual either output may be NULL.                     */
+ * no separate u2_cast_bf16 pass is needed; in u2_bn_bwd_apply_dual either output may be NULL.
+ * residual != NULL: y = relu(bn(x) + residual), the tail of core/models/build_blocks.py ResidualBlock.forward; its
+ * backward passes the saved y as out_mask (ReLU mask = y > 0 instead of the recomputed sign of bn(x)) and gets the
+ * gradient of the residual input in dresidual (= the masked output gradient).                                   */
 size_t u2_conv_tile_stats_parts(int64_t rows);
 int u2_conv_fwd_stats(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
                       const int32_t *table, const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd,
@@ -208,11 +211,12 @@ int u2_conv_fwd_stats(const float *X, int64_t n_src, int32_t Cs, const float *W,
 int u2_bn_stats_from_tiles(const float *tile_stats, int64_t n_parts, int32_t C, int64_t n, double *sums,
                            u2_stream_t stream);
 int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
-                     const float *gamma, const float *beta, int32_t relu, float *y, void *y_bf16, float *save_mean,
-                     float *save_invstd, float *running_mean, float *running_var, u2_stream_t stream);
+                     const float *gamma, const float *beta, int32_t relu, const float *residual, float *y, void *y_bf16,
+                     float *save_mean, float *save_invstd, float *running_mean, float *running_var, u2_stream_t stream);
 int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
                          const float *gamma, const float *beta, const double *dsum, const double *count_dev,
-                         int32_t relu, float *dx, void *dx_bf16, u2_stream_t stream);
+                         int32_t relu, const float *out_mask, float *dresidual, float *dx, void *dx_bf16,
+                         u2_stream_t stream);
 
 /* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
 int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);

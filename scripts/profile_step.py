@@ -42,8 +42,9 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(2):
         step(*pool[i % 2])
     torch.cuda.synchronize()
-ev = [e for e in prof.key_averages() if e.device_time_total > 0]
+from torch.autograd import DeviceType
+ev = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA and e.self_device_time_total > 0]
 tot = sum(e.self_device_time_total for e in ev)
-print(f"total device time {tot/2e3:.2f} ms/step")
-for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:45]:
+print(f"total kernel time {tot/2e3:.2f} ms/step over {sum(e.count for e in ev)//2} launches")
+for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:90]:
     print(f"{e.self_device_time_total/2e3:9.3f} ms/step  x{e.count//2:4d}  {e.key[:110]}")

@@ -300,3 +300,41 @@ def test_spvcnn_fused_conv_bn_vs_unfused(tc):
             assert rel_err(b[3][k], a[3][k]) < TF32_REL, k
     finally:
         tc.set_math("fp32")
+
+
+@pytest.mark.parametrize("inc,outc", [(64, 64), (64, 96), (192, 192)])
+def test_fused_residual_block_matches_unfused(tc, inc, outc):
+    """ResidualBlock (core/models/build_blocks.py:53-84): relu(net(x) + downsample(x)) folded into the last conv's
+    BatchNorm epilogue, against the same block with separate add / ReLU passes."""
+    from u2mkd_b200 import fusion, models
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(inc + outc)
+    c = rand_coords(rng, 5000).cuda()
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], inc)).astype(np.float32)).cuda()
+    tc.set_math("bf16")
+    try:
+        res = []
+        for fused in (False, True):
+            torch.manual_seed(2)
+            blk = models.product().ResidualBlock(inc, outc).cuda()
+            with torch.no_grad():
+                for m in blk.modules():
+                    if isinstance(m, torch.nn.BatchNorm1d):
+                        m.weight.uniform_(0.5, 1.5)
+                        m.bias.uniform_(-0.3, 0.3)
+            fusion.optimize(blk, fuse_residual=fused)
+            assert ("forward" in blk.__dict__) == fused
+            x = gts.SparseTensor(f.clone().requires_grad_(True), c)
+            y = blk(x)
+            g = torch.from_numpy(np.random.default_rng(9).standard_normal(tuple(y.F.shape)).astype(np.float32)).cuda()
+            y.F.backward(g)
+            grads = [p.grad.clone() for _, p in sorted(blk.named_parameters())]
+            res.append((y.F.detach(), x.F.grad, grads, getattr(y.F, "_u2_bf16", None)))
+        a, b = res
+        assert float(b[0].min()) >= 0.0 and b[3] is not None and torch.equal(b[3][0], b[0].bfloat16())
+        assert rel_err(b[0], a[0]) < 1e-3
+        assert rel_err(b[1], a[1]) < 2e-3
+        for ga, gb in zip(a[2], b[2]):
+            assert rel_err(gb, ga) < 2e-3
+    finally:
+        tc.set_math("fp32")

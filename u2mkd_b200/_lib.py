@@ -86,13 +86,13 @@ _SIGNATURES = {
     "u2_conv_tile_stats_parts": (ctypes.c_size_t, [_i64]),
     "u2_conv_fwd_stats": (ctypes.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _sz, _p, _sz, _p]),
     "u2_bn_stats_from_tiles": (ctypes.c_int, [_p, _i64, _i32, _i64, _p, _p]),
-    "u2_bn_apply_dual": (ctypes.c_int, [_p, _i64, _i32, _p, _f, _f, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "u2_bn_bwd_apply_dual": (ctypes.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
+    "u2_bn_apply_dual": (ctypes.c_int, [_p, _i64, _i32, _p, _f, _f, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "u2_bn_bwd_apply_dual": (ctypes.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "u2_bn_supported": (ctypes.c_int, [_i32]),
     "u2_bn_scratch_bytes": (ctypes.c_size_t, [_i32]),
     "u2_bn_stats": (ctypes.c_int, [_p, _i64, _i32, _p, _p, _sz, _p]),
     "u2_bn_apply": (ctypes.c_int, [_p, _i64, _i32, _p, _f, _f, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
-    "u2_bn_bwd_reduce": (ctypes.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p, _sz, _p]),
+    "u2_bn_bwd_reduce": (ctypes.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "u2_bn_bwd_apply": (ctypes.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "u2_cast_bf16": (ctypes.c_int, [_p, _i64, _p, _p]),
     "u2_kmap_pairs_scratch_bytes": (_sz, [_i64]),

@@ -128,7 +128,8 @@ template <bool RELU, int U>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict__ x, int64_t n, int tx, int ty,
                                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                       float4 *__restrict__ y, uint2 *__restrict__ yb) {
+                                                       const float4 *__restrict__ res, float4 *__restrict__ y,
+                                                       uint2 *__restrict__ yb) {
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
     const int c = cx * 4;
     float4 sc, sh;
@@ -140,6 +141,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict_
     const int64_t step = (int64_t)gridDim.x * ty;
     auto put = [&](int64_t i, const float4 v) {
         float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+        if (res) {  // residual branch of a ResidualBlock: relu(bn(conv(x)) + shortcut(x)) in one pass
+            const float4 rr = __ldg(res + i);
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
         if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         y[i] = o;
         if (yb) yb[i] = bf16x4(o);  // the next conv's bf16 operand, written while the row is in registers
@@ -163,19 +168,28 @@ template <bool RELU, int U>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ x,
                                                             int64_t n, int tx, int ty, const float *__restrict__ mean,
                                                             const float *__restrict__ invstd, const float *__restrict__ gamma,
-                                                            const float *__restrict__ beta, float *__restrict__ part) {
+                                                            const float *__restrict__ beta, const float4 *__restrict__ zout,
+                                                            float *__restrict__ part) {
     extern __shared__ float4 s_red[];
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
     const int c = cx * 4;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto f = [&](float4 v, float4 d) {
+    auto f = [&](float4 v, float4 d, int64_t i) {
         const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
         if (RELU) {
-            if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
-            if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
-            if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
-            if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
+            if (zout) {  // a residual was added before the ReLU: the mask is the sign of the saved output
+                const float4 z = __ldg(zout + i);
+                if (z.x <= 0.f) d.x = 0.f;
+                if (z.y <= 0.f) d.y = 0.f;
+                if (z.z <= 0.f) d.z = 0.f;
+                if (z.w <= 0.f) d.w = 0.f;
+            } else {
+                if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
+                if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
+                if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
+                if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
+            }
         }
         acc4(s, d);
         q.x += d.x * h.x; q.y += d.y * h.y; q.z += d.z * h.z; q.w += d.w * h.w;
@@ -190,9 +204,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4 *__rest
         for (int u = 0; u < U; u++) { v[u] = __ldg(x + i + u * pstep); d[u] = __ldg(dy + i + u * pstep); }
         BN_LOADS_FIRST();
 #pragma unroll
-        for (int u = 0; u < U; u++) f(v[u], d[u]);
+        for (int u = 0; u < U; u++) f(v[u], d[u], i + u * pstep);
     }
-    for (; r < n; r += step, i += pstep) f(__ldg(x + i), __ldg(dy + i));
+    for (; r < n; r += step, i += pstep) f(__ldg(x + i), __ldg(dy + i), i);
     block_reduce_to_partials(s, q, tx, ty, cx, ry, s_red, part);
 }
 
@@ -202,7 +216,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4 *__restr
                                                            int64_t n, int tx, int ty, const float *__restrict__ mean,
                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                            const float *__restrict__ beta, const double *__restrict__ dsum,
-                                                           const double *__restrict__ count, float4 *__restrict__ dx,
+                                                           const double *__restrict__ count, const float4 *__restrict__ zout,
+                                                           float4 *__restrict__ dres, float4 *__restrict__ dx,
                                                            uint2 *__restrict__ dxb) {
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
     const int C = tx * 4, c = cx * 4;
@@ -213,14 +228,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4 *__restr
     const float4 bb = make_float4((float)(dsum[C + c] * inv_count), (float)(dsum[C + c + 1] * inv_count),
                                   (float)(dsum[C + c + 2] * inv_count), (float)(dsum[C + c + 3] * inv_count));
     const float4 gi = make_float4(g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w);
-    auto f = [&](float4 v, float4 d) {
+    auto f = [&](float4 v, float4 d, int64_t i) {
         const float4 h = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
         if (RELU) {
-            if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
-            if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
-            if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
-            if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
+            if (zout) {
+                const float4 z = __ldg(zout + i);
+                if (z.x <= 0.f) d.x = 0.f;
+                if (z.y <= 0.f) d.y = 0.f;
+                if (z.z <= 0.f) d.z = 0.f;
+                if (z.w <= 0.f) d.w = 0.f;
+            } else {
+                if (h.x * g.x + b.x <= 0.f) d.x = 0.f;
+                if (h.y * g.y + b.y <= 0.f) d.y = 0.f;
+                if (h.z * g.z + b.z <= 0.f) d.z = 0.f;
+                if (h.w * g.w + b.w <= 0.f) d.w = 0.f;
+            }
         }
+        if (dres) dres[i] = d;  // gradient of the residual input = the masked output gradient
         return make_float4(gi.x * (d.x - a.x - h.x * bb.x), gi.y * (d.y - a.y - h.y * bb.y), gi.z * (d.z - a.z - h.z * bb.z),
                            gi.w * (d.w - a.w - h.w * bb.w));
     };
@@ -238,9 +262,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4 *__restr
         for (int u = 0; u < U; u++) { v[u] = __ldg(x + i + u * pstep); d[u] = __ldg(dy + i + u * pstep); }
         BN_LOADS_FIRST();
 #pragma unroll
-        for (int u = 0; u < U; u++) put(i + u * pstep, f(v[u], d[u]));
+        for (int u = 0; u < U; u++) put(i + u * pstep, f(v[u], d[u], i + u * pstep));
     }
-    for (; r < n; r += step, i += pstep) put(i, f(__ldg(x + i), __ldg(dy + i)));
+    for (; r < n; r += step, i += pstep) put(i, f(__ldg(x + i), __ldg(dy + i), i));
 }
 
 // sums[c] += sum_p part[p][0][c], sums[C + c] += sum_p part[p][1][c]: the per-warp column sums the conv
@@ -326,13 +350,15 @@ extern "C" int u2_bn_stats_from_tiles(const float *tile_stats, int64_t n_parts, 
 }
 
 extern "C" int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
-                                const float *gamma, const float *beta, int32_t relu, float *y, void *y_bf16,
+                                const float *gamma, const float *beta, int32_t relu, const float *residual, float *y,
+                                void *y_bf16,
                                 float *save_mean, float *save_invstd, float *running_mean, float *running_var,
                                 u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(u2_bn_supported(C), "u2_bn_apply: C=%d", C);
     U2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)save_mean |
-                   (uintptr_t)save_invstd | (uintptr_t)y_bf16) & 15) == 0, "u2_bn_apply: pointers must be 16-byte aligned");
+                   (uintptr_t)save_invstd | (uintptr_t)y_bf16 | (uintptr_t)residual) & 15) == 0,
+                 "u2_bn_apply: pointers must be 16-byte aligned");
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, eps, momentum, save_mean, save_invstd, running_mean,
                                                          running_var);
     U2_LAUNCH_OK();
@@ -342,10 +368,12 @@ extern "C" int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const doub
     const unsigned grid = bn_grid(n, g, cap);
     if (relu)
         BN_DISPATCH_U(unroll, (bn_apply_kernel<true, UU><<<grid, g.tx * g.ty, 0, st>>>(
-            (const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y, (uint2 *)y_bf16)));
+            (const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (const float4 *)residual, (float4 *)y,
+            (uint2 *)y_bf16)));
     else
         BN_DISPATCH_U(unroll, (bn_apply_kernel<false, UU><<<grid, g.tx * g.ty, 0, st>>>(
-            (const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (float4 *)y, (uint2 *)y_bf16)));
+            (const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (const float4 *)residual, (float4 *)y,
+            (uint2 *)y_bf16)));
     U2_LAUNCH_OK();
     return 0;
 }
@@ -353,14 +381,15 @@ extern "C" int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const doub
 extern "C" int u2_bn_apply(const float *x, int64_t n, int32_t C, const double *sums, float eps, float momentum,
                            const float *gamma, const float *beta, int32_t relu, float *y, float *save_mean,
                            float *save_invstd, float *running_mean, float *running_var, u2_stream_t stream) {
-    return u2_bn_apply_dual(x, n, C, sums, eps, momentum, gamma, beta, relu, y, nullptr, save_mean, save_invstd, running_mean,
-                            running_var, stream);
+    return u2_bn_apply_dual(x, n, C, sums, eps, momentum, gamma, beta, relu, nullptr, y, nullptr, save_mean, save_invstd,
+                            running_mean, running_var, stream);
 }
 
 // dsum: fp64 [2C], zeroed by the call: dsum[c] = sum dz (= grad beta), dsum[C+c] = sum dz*xhat (= grad gamma)
 extern "C" int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int32_t C, const float *mean,
-                                const float *invstd, const float *gamma, const float *beta, int32_t relu, double *dsum,
-                                void *scratch, size_t scratch_bytes, u2_stream_t stream) {
+                                const float *invstd, const float *gamma, const float *beta, int32_t relu,
+                                const float *out_mask, double *dsum, void *scratch, size_t scratch_bytes,
+                                u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(u2_bn_supported(C), "u2_bn_bwd_reduce: C=%d", C);
     U2_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy) & 15) == 0, "u2_bn_bwd_reduce: pointers must be 16-byte aligned");
@@ -375,10 +404,11 @@ extern "C" int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int3
         const size_t smem = 2 * threads * sizeof(float4);
         if (relu)
             BN_DISPATCH_U(unroll, (bn_bwd_reduce_kernel<true, UU><<<grid, threads, smem, st>>>(
-                (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, (float *)scratch)));
+                (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, (const float4 *)out_mask,
+                (float *)scratch)));
         else
             BN_DISPATCH_U(unroll, (bn_bwd_reduce_kernel<false, UU><<<grid, threads, smem, st>>>(
-                (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, (float *)scratch)));
+                (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, nullptr, (float *)scratch)));
         U2_LAUNCH_OK();
     }
     return bn_fold_partials((const float *)scratch, grid, C, dsum, -1.0, st);
@@ -386,23 +416,25 @@ extern "C" int u2_bn_bwd_reduce(const float *dy, const float *x, int64_t n, int3
 
 extern "C" int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, const float *mean,
                                     const float *invstd, const float *gamma, const float *beta, const double *dsum,
-                                    const double *count_dev, int32_t relu, float *dx, void *dx_bf16, u2_stream_t stream) {
+                                    const double *count_dev, int32_t relu, const float *out_mask, float *dresidual,
+                                    float *dx, void *dx_bf16, u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     U2_CHECK_ARG(u2_bn_supported(C), "u2_bn_bwd_apply: C=%d", C);
     U2_CHECK_ARG(dx || dx_bf16, "u2_bn_bwd_apply: no output");
-    U2_CHECK_ARG((((uintptr_t)dx | (uintptr_t)dx_bf16) & 15) == 0, "u2_bn_bwd_apply: outputs must be 16-byte aligned");
+    U2_CHECK_ARG((((uintptr_t)dx | (uintptr_t)dx_bf16 | (uintptr_t)out_mask | (uintptr_t)dresidual) & 15) == 0,
+                 "u2_bn_bwd_apply: pointers must be 16-byte aligned");
     if (n == 0) return 0;
     const BnGeom g = bn_geom(C);
     static const int cap = bn_env("U2_BN_CAP_BAPPLY", 4), unroll = bn_env("U2_BN_U_BAPPLY", 2);
     const unsigned grid = bn_grid(n, g, cap);
     if (relu)
         BN_DISPATCH_U(unroll, (bn_bwd_apply_kernel<true, UU><<<grid, g.tx * g.ty, 0, st>>>(
-            (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, dsum, count_dev, (float4 *)dx,
-            (uint2 *)dx_bf16)));
+            (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, dsum, count_dev,
+            (const float4 *)out_mask, (float4 *)dresidual, (float4 *)dx, (uint2 *)dx_bf16)));
     else
         BN_DISPATCH_U(unroll, (bn_bwd_apply_kernel<false, UU><<<grid, g.tx * g.ty, 0, st>>>(
-            (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, dsum, count_dev, (float4 *)dx,
-            (uint2 *)dx_bf16)));
+            (const float4 *)dy, (const float4 *)x, n, g.tx, g.ty, mean, invstd, gamma, beta, dsum, count_dev, nullptr,
+            (float4 *)dresidual, (float4 *)dx, (uint2 *)dx_bf16)));
     U2_LAUNCH_OK();
     return 0;
 }
@@ -410,5 +442,6 @@ extern "C" int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, 
 extern "C" int u2_bn_bwd_apply(const float *dy, const float *x, int64_t n, int32_t C, const float *mean, const float *invstd,
                                const float *gamma, const float *beta, const double *dsum, const double *count_dev,
                                int32_t relu, float *dx, u2_stream_t stream) {
-    return u2_bn_bwd_apply_dual(dy, x, n, C, mean, invstd, gamma, beta, dsum, count_dev, relu, dx, nullptr, stream);
+    return u2_bn_bwd_apply_dual(dy, x, n, C, mean, invstd, gamma, beta, dsum, count_dev, relu, nullptr, nullptr, dx, nullptr,
+                                stream);
 }

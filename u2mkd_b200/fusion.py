@@ -7,7 +7,9 @@ model (core/models/build_blocks.py:21-84) and only changes how two kinds of modu
   * a ReLU that directly follows such a module inside an nn.Sequential is folded into it;
   * a BatchNorm(+ReLU) that directly follows a sparse Conv3d inside an nn.Sequential runs as that conv's
     epilogue (ops.ConvBNReLUFn): statistics from the conv kernel, bf16 operands for the next conv and for
-    the backward convs written by the BatchNorm kernels instead of separate cast passes.
+    the backward convs written by the BatchNorm kernels instead of separate cast passes;
+  * the tail of a ResidualBlock, relu(net(x) + downsample(x)) (core/models/build_blocks.py:53-84), runs inside the
+    BatchNorm epilogue of net's last conv: no separate add / ReLU passes over the block output.
 """
 from __future__ import annotations
 
@@ -58,7 +60,31 @@ def _is_sparse_conv(m) -> bool:
     return isinstance(m, Conv3d)
 
 
-def optimize(model: nn.Module, fuse_relu: bool = True, fuse_conv_bn: bool = True) -> nn.Module:
+def _residual_forward(block):
+    """forward of a ResidualBlock whose `net` ends in (Conv3d with a BatchNorm epilogue, absorbed BatchNorm)."""
+    head, last_conv = list(block.net.children())[:-2], list(block.net.children())[-2]
+
+    def forward(x):
+        shortcut = block.downsample(x)
+        h = x
+        for m in head:
+            h = m(h)
+        return last_conv(h, residual=shortcut.feats, relu=True)
+
+    return forward
+
+
+def _is_residual_block(m) -> bool:
+    if type(m).__name__ != "ResidualBlock" or not all(hasattr(m, a) for a in ("net", "downsample", "relu")):
+        return False
+    if not isinstance(m.net, nn.Sequential) or not isinstance(m.relu, nn.ReLU) or len(m.net) < 2:
+        return False
+    kids = list(m.net.children())
+    return (_is_sparse_conv(kids[-2]) and getattr(kids[-2], "_u2_epilogue", None) is not None
+            and kids[-2]._u2_epilogue[0] is kids[-1] and not kids[-2]._u2_epilogue[1] and "forward" not in m.__dict__)
+
+
+def optimize(model: nn.Module, fuse_relu: bool = True, fuse_conv_bn: bool = True, fuse_residual: bool = True) -> nn.Module:
     """In-place; returns the model. Safe to call once, after any SyncBatchNorm conversion."""
     if fuse_relu:
         for seq in model.modules():
@@ -84,4 +110,8 @@ def optimize(model: nn.Module, fuse_relu: bool = True, fuse_conv_bn: bool = True
                     # a tuple keeps `b` out of a's submodule registry (state_dict keys unchanged)
                     a._u2_epilogue = (b, bool(getattr(b, "_u2_fused_relu", False)))
                     b._u2_absorbed = True
+        if fuse_residual:
+            for m in model.modules():
+                if _is_residual_block(m):
+                    m.forward = _residual_forward(m)  # instance attribute: the class and its state_dict stay as they are
     return model

@@ -524,9 +524,10 @@ class BatchNormFn(Function):
         dsum = torch.empty(2 * c, dtype=torch.float64, device=x.device)
         scratch = _bn_scratch(c, x.device)
         check(lib().u2_bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), scratch.data_ptr(),
-                                     scratch.numel(), st))
-        dbeta, dgamma = dsum[:c].float(), dsum[c:].float()   # local sums: DDP averages parameter grads
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), None, dsum.data_ptr(),
+                                     scratch.data_ptr(), scratch.numel(), st))
+        dparam = dsum.float()   # local sums: DDP averages parameter grads
+        dbeta, dgamma = dparam[:c], dparam[c:]
         if group is not None:
             dsum = dsum.clone()
             torch.distributed.all_reduce(dsum, group=group)
@@ -560,8 +561,8 @@ class ConvBNReLUFn(Function):
     gradient of Y never exists."""
 
     @staticmethod
-    def forward(ctx, feats, feats_bf16, weight, gamma, beta, running_mean, running_var, momentum, eps, relu, group,
-                kmap: KernelMap, transposed: bool):
+    def forward(ctx, feats, feats_bf16, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, relu,
+                group, kmap: KernelMap, transposed: bool):
         K, cin, cout = weight.shape
         weight = weight.contiguous()
         if not transposed:
@@ -592,22 +593,28 @@ class ConvBNReLUFn(Function):
         zb = torch.empty((n_dst, cout), dtype=torch.bfloat16, device=dev)
         mean = torch.empty(cout, dtype=torch.float32, device=dev)
         invstd = torch.empty(cout, dtype=torch.float32, device=dev)
+        if residual is not None:
+            residual = residual.contiguous()
+            assert residual.shape == y.shape and residual.dtype == torch.float32, (residual.shape, y.shape)
         check(lib().u2_bn_apply_dual(y.data_ptr(), n_dst, cout, sums.data_ptr(), float(eps), float(momentum),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), z.data_ptr(), zb.data_ptr(),
-                                     mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean), _ptr(running_var), _st()))
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(residual), z.data_ptr(),
+                                     zb.data_ptr(), mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean),
+                                     _ptr(running_var), _st()))
         _count(5)
-        ctx.save_for_backward(feats_bf16, weight, y, gamma, beta, mean, invstd, sums)
-        ctx.misc = (kmap, transposed, relu, group)
+        # with a residual the ReLU mask cannot be recomputed from y alone: keep the output z for it
+        ctx.save_for_backward(feats_bf16, weight, y, gamma, beta, mean, invstd, sums,
+                              z if (residual is not None and relu) else None)
+        ctx.misc = (kmap, transposed, relu, group, residual is not None)
         ctx.mark_non_differentiable(zb)
         ctx.set_materialize_grads(False)  # no zero-filled "gradient" for the bf16 copy
         return z, zb
 
     @staticmethod
     def backward(ctx, dz, _dzb):
-        xb, weight, y, gamma, beta, mean, invstd, sums = ctx.saved_tensors
-        kmap, transposed, relu, group = ctx.misc
+        xb, weight, y, gamma, beta, mean, invstd, sums, zmask = ctx.saved_tensors
+        kmap, transposed, relu, group, has_res = ctx.misc
         if dz is None:
-            return (None,) * 13
+            return (None,) * 14
         dz = dz.contiguous().float()
         K, cin, cout = weight.shape
         n, c = y.shape
@@ -615,16 +622,22 @@ class ConvBNReLUFn(Function):
         dsum = torch.empty(2 * c, dtype=torch.float64, device=dev)
         scratch = _bn_scratch(c, dev)
         check(lib().u2_bn_bwd_reduce(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), dsum.data_ptr(), scratch.data_ptr(),
-                                     scratch.numel(), _st()))
-        dbeta, dgamma = dsum[:c].float(), dsum[c:].float()
+                                     gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(zmask), dsum.data_ptr(),
+                                     scratch.data_ptr(), scratch.numel(), _st()))
+        dparam = dsum.float()
+        dbeta, dgamma = dparam[:c], dparam[c:]
         if group is not None:
             dsum = dsum.clone()
             torch.distributed.all_reduce(dsum, group=group)
         dyb = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+        dres = None
+        if has_res and ctx.needs_input_grad[5]:
+            # without a ReLU the residual's gradient is dz itself; with one, the masked dz written by the kernel
+            dres = torch.empty_like(dz) if relu else dz
         check(lib().u2_bn_bwd_apply_dual(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
                                          gamma.data_ptr(), beta.data_ptr(), dsum.data_ptr(), sums.data_ptr() + 16 * c,
-                                         int(relu), None, dyb.data_ptr(), _st()))
+                                         int(relu), _ptr(zmask), dres.data_ptr() if (dres is not None and relu) else None,
+                                         None, dyb.data_ptr(), _st()))
         _count(3)
         grad_feats = grad_weight = None
         if ctx.needs_input_grad[0]:
@@ -637,7 +650,7 @@ class ConvBNReLUFn(Function):
             _timed("wgrad", kmap, n, K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
                 xb.data_ptr(), cin, dyb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
                 flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, _st())))
-        return (grad_feats, None, grad_weight, dgamma, dbeta) + (None,) * 8
+        return (grad_feats, None, grad_weight, dgamma, dbeta, dres) + (None,) * 8
 
 
 def _bn_group(bn):
@@ -650,9 +663,9 @@ def _bn_group(bn):
     return None
 
 
-def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, relu: bool):
-    """conv3d -> bn(+relu) on feature matrices. Fused node where the bf16 tcgen05 kernels cover the layer,
-    otherwise the two separate operators (same results up to summation order)."""
+def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, relu: bool, residual=None):
+    """conv3d -> bn [-> + residual] (-> relu) on feature matrices. Fused node where the bf16 tcgen05 kernels cover
+    the layer, otherwise the separate operators (same results up to summation order)."""
     group = _bn_group(bn)
     K, cin, cout = weight.shape
     n_dst = kmap.n_in if transposed else kmap.n_out
@@ -664,15 +677,18 @@ def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, re
              and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, MATH_BF16)
              and (cout // ((cout + 255) // 256)) % 32 == 0)
     if not fused:
-        return batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, relu, group)
+        if residual is None:
+            return batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, relu, group)
+        out = batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, False, group) + residual
+        return torch.relu_(out) if relu else out
     momentum = 0.1 if bn.momentum is None else bn.momentum
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     feats = feats.contiguous()
-    z, zb = ConvBNReLUFn.apply(feats, bf16_view(feats), weight, bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu,
-                               group, kmap, transposed)
+    z, zb = ConvBNReLUFn.apply(feats, bf16_view(feats), weight, bn.weight, bn.bias, residual, rm, rv, momentum, bn.eps,
+                               relu, group, kmap, transposed)
     stash_bf16(z, zb)
     return z
 

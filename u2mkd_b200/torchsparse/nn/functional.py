@@ -35,11 +35,13 @@ def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1)
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, stride=1, dilation=1,
-           transposed: bool = False, epilogue=None) -> SparseTensor:
+           transposed: bool = False, epilogue=None, residual=None) -> SparseTensor:
     """F.conv3d of torchsparse v1.4.0: kernel-map lookup/build, then
     one fused gather-GEMM kernel (ops.ConvolutionFn) instead of K gather/mm/scatter rounds.
     `epilogue=(bn_module, relu)` (set by u2mkd_b200.fusion.optimize, not part of the torchsparse signature)
-    applies that BatchNorm(+ReLU) to the result inside the same autograd node."""
+    applies that BatchNorm(+ReLU) to the result inside the same autograd node; `residual` (a feature matrix,
+    only with an epilogue) is added between the BatchNorm and the ReLU (ResidualBlock tail)."""
+    assert residual is None or epilogue is not None
     feats, coords = input.feats, input.coords
     kernel_size, stride, dilation = (make_ntuple(v, ndim=3) for v in (kernel_size, stride, dilation))
     unit = (1, 1, 1)
@@ -59,7 +61,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
         elif any(s > 1 for s in stride):
             coords = input.cmaps[out_stride]  # upstream skips this on a cache hit
         if epilogue is not None and bias is None:
-            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, False, *epilogue)
+            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, False, *epilogue, residual=residual)
             epilogue = None
         else:
             feats = ops.sparse_conv(feats, weight, kmap, transposed=False)
@@ -67,7 +69,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
         out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
         kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
         if epilogue is not None and bias is None:
-            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, True, *epilogue)
+            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, True, *epilogue, residual=residual)
             epilogue = None
         else:
             feats = ops.sparse_conv(feats, weight, kmap, transposed=True)
@@ -75,7 +77,11 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
     if bias is not None:
         feats = feats + bias
     if epilogue is not None:  # 1x1x1 kernels and biased convs: the separate BatchNorm kernels
-        feats = ops.batch_norm_relu(feats, epilogue[0], epilogue[1], ops._bn_group(epilogue[0]))
+        if residual is None:
+            feats = ops.batch_norm_relu(feats, epilogue[0], epilogue[1], ops._bn_group(epilogue[0]))
+        else:
+            feats = ops.batch_norm_relu(feats, epilogue[0], False, ops._bn_group(epilogue[0])) + residual
+            feats = torch.relu_(feats) if epilogue[1] else feats
     output = SparseTensor(coords=coords, feats=feats, stride=out_stride)
     output.cmaps = input.cmaps
     output.cmaps.setdefault(output.stride, output.coords)

@@ -55,9 +55,14 @@ class Conv3d(nn.Module):
         if self.bias is not None:
             self.bias.data.uniform_(-std, std)
 
-    def forward(self, input: SparseTensor) -> SparseTensor:
+    def forward(self, input: SparseTensor, residual=None, relu=None) -> SparseTensor:
+        """`residual` / `relu` are used by u2mkd_b200.fusion only (ResidualBlock tail folded into this conv's
+        BatchNorm epilogue); the torchsparse call signature is forward(input)."""
+        epilogue = getattr(self, "_u2_epilogue", None)
+        if epilogue is not None and relu is not None:
+            epilogue = (epilogue[0], bool(relu))
         return F.conv3d(input, self.kernel, kernel_size=self.kernel_size, bias=self.bias, stride=self.stride,
-                        dilation=self.dilation, transposed=self.transposed, epilogue=getattr(self, "_u2_epilogue", None))
+                        dilation=self.dilation, transposed=self.transposed, epilogue=epilogue, residual=residual)
 
 
 class BatchNorm(nn.BatchNorm1d):
