@@ -263,17 +263,28 @@ def test_spvcnn_fwd_bwd_vs_oracle(gpu, oracle, cr, vs, seeds):
     out_o = step(net_o, oracle.SparseTensor, "cpu")
     # 49 conv + BN layers deep: BN re-normalises, so errors do not grow, but summation order differs
     assert rel_err(out_g, out_o) < 1e-3
+    # Gradients: the fp32 oracle itself is ~2e-3 (worst tensor, max-norm) away from the same oracle run in fp64,
+    # so "GPU vs fp32 oracle" only compares two roundings of one quantity.  The fp64 oracle is the truth: the GPU
+    # path has to be as close to it as the fp32 CPU restatement is (factor 3), and within 1e-2 outright.
+    net_t = models.build_family(oracle.as_torchsparse_modules()["torchsparse"]).SPVCNN(cr=cr, pres=vs, vres=vs)
+    net_t.load_state_dict(net_o.state_dict())
+    net_t.double()
+    net_t.dropout = torch.nn.Identity()
+    x_t = oracle.SparseTensor(torch.from_numpy(feats).double(), torch.from_numpy(coords))
+    torch.nn.functional.cross_entropy(net_t({"lidar": x_t})["x_vox"], target).backward()
     # a Linear/conv bias directly in front of a BatchNorm has an exactly-zero true gradient: what is
-    # left there is rounding noise on both sides, so parameters whose oracle gradient is < 1e-6 of
+    # left there is rounding noise on both sides, so parameters whose true gradient is < 1e-6 of
     # the largest gradient in the model are compared absolutely instead of relatively
-    gmax = max(float(p.grad.abs().max()) for p in net_o.parameters())
-    worst = 0.0
-    for (name, pg), (_, po) in zip(net_g.named_parameters(), net_o.named_parameters()):
-        if float(po.grad.abs().max()) < 1e-6 * gmax:
-            assert float((pg.grad.cpu() - po.grad).abs().max()) < 1e-6 * gmax, name
+    gmax = max(float(p.grad.abs().max()) for p in net_t.parameters())
+    worst_g = worst_o = 0.0
+    for (name, pg), (_, po), (_, pt) in zip(net_g.named_parameters(), net_o.named_parameters(),
+                                            net_t.named_parameters()):
+        if float(pt.grad.abs().max()) < 1e-6 * gmax:
+            assert float((pg.grad.cpu().double() - pt.grad).abs().max()) < 1e-6 * gmax, name
         else:
-            worst = max(worst, rel_err(pg.grad, po.grad))
-    assert worst < 5e-3, worst
+            worst_g = max(worst_g, rel_err(pg.grad, pt.grad))
+            worst_o = max(worst_o, rel_err(po.grad, pt.grad))
+    assert worst_g < max(3.0 * worst_o, 1e-3) and worst_g < 1e-2, (worst_g, worst_o)
 
 
 def test_cpu_tensor_is_rejected(gpu):
