@@ -290,6 +290,8 @@ def test_spvcnn_fused_conv_bn_vs_unfused(tc):
             assert (n_fused > 30) == fused
             out = net({"lidar": gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())})["x_vox"]
             out.square().mean().backward()
+            # counters are bumped once per forward by one multi-tensor add (fusion.optimize), not per layer
+            assert all(int(v) == 1 for k, v in net.state_dict().items() if k.endswith("num_batches_tracked"))
             convs = [m for m in net.modules() if isinstance(m, gts.nn.Conv3d) and m.kernel.grad is not None]
             outs.append((out.detach(), convs[5].kernel.grad.clone(), convs[-3].kernel.grad.clone(),
                          {k: v.clone() for k, v in net.state_dict().items() if "running_var" in k}))

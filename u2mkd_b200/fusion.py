@@ -99,6 +99,10 @@ def optimize(model: nn.Module, fuse_relu: bool = True, fuse_conv_bn: bool = True
     for m in model.modules():
         if isinstance(m, _BN_TYPES) and not isinstance(m, _FusedNormMixin):
             m.__class__ = _fused_class(m.__class__)
+            m._u2_lazy_counter = True  # num_batches_tracked of all layers: one multi-tensor add per forward
+    if not getattr(model, "_u2_counter_hook", False):
+        model.register_forward_hook(lambda *_: ops.flush_bn_counters())
+        model._u2_counter_hook = True
     if fuse_conv_bn:
         for seq in model.modules():
             if not isinstance(seq, nn.Sequential):

@@ -483,6 +483,27 @@ def sparse_conv(feats, weight, kmap: KernelMap, transposed: bool = False, math: 
 
 
 # -------------------------------------------------------------------------------- batch norm (+ReLU)
+_pending_counters = []
+
+
+def _count_batch(bn) -> None:
+    """num_batches_tracked += 1.  Modules marked by fusion.optimize defer it to the end of the model's forward,
+    where all counters are bumped by one multi-tensor kernel instead of one tiny kernel per layer."""
+    if not bn.track_running_stats or bn.num_batches_tracked is None:
+        return
+    if getattr(bn, "_u2_lazy_counter", False) and len(_pending_counters) < 4096:
+        _pending_counters.append(bn.num_batches_tracked)
+    else:
+        bn.num_batches_tracked.add_(1)
+
+
+def flush_bn_counters() -> None:
+    if _pending_counters:
+        torch._foreach_add_(_pending_counters, 1)
+        _count()
+        _pending_counters.clear()
+
+
 def _bn_scratch(c: int, device) -> torch.Tensor:
     """Per-CTA partial sums of the two BatchNorm reductions (stream-ordered allocation from torch's pool)."""
     return torch.empty(lib().u2_bn_scratch_bytes(c), dtype=torch.uint8, device=device)
@@ -682,8 +703,7 @@ def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, re
         out = batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, False, group) + residual
         return torch.relu_(out) if relu else out
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    if bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    _count_batch(bn)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     feats = feats.contiguous()
@@ -703,8 +723,7 @@ def batch_norm_relu(x, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = F
     if (bn.training and x.is_cuda and bn.affine and x.dtype == torch.float32 and lib().u2_bn_supported(c)
             and x.shape[0] > 0):
         momentum = 0.1 if bn.momentum is None else bn.momentum
-        if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        _count_batch(bn)
         rm = bn.running_mean if bn.track_running_stats else None
         rv = bn.running_var if bn.track_running_stats else None
         return BatchNormFn.apply(x, bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu, group)
