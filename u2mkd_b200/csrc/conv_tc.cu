@@ -15,6 +15,7 @@
 //   No gather buffer, no output read-modify-write, no atomics: every output row is written
 //   once; (tile, offset) pairs without neighbours are skipped.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "u2_common.cuh"
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
     const int nt = blockIdx.y;
-    long long *dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    long long *dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
     const int n_cc = p.Cs * ES / ROWB;
     const int n_nt = p.Cd / NT;
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         const uint32_t dst0 = (uint32_t)(chunk * A_LBO + (tid / CHUNKS) * 16);
         int s = 0;
         uint32_t ph = 0;
+        long long dbg_wait = 0;
         for (uint32_t m = kmask; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
             const int *tab_k = s_tab + k * TILE_M + tid / CHUNKS;
@@ -288,7 +290,13 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             }
             const uint8_t *xc = p.X;
             for (int cc = 0; cc < n_cc; cc++, xc += ROWB) {
-                mbar_wait(s_empty + s, ph ^ 1u);
+                if (dbg && tid == 0) {
+                    const long long t0 = clock64();
+                    mbar_wait(s_empty + s, ph ^ 1u);
+                    dbg_wait += clock64() - t0;
+                } else {
+                    mbar_wait(s_empty + s, ph ^ 1u);
+                }
                 const uint32_t a_dst = smem_u32(s_stage + (size_t)s * stage_bytes) + dst0;
 #pragma unroll
                 for (int i = 0; i < CHUNKS; i++) {
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             }
         }
         // ============================ epilogue ============================
-        if (dbg && tid == 0) dbg[2] = clock64();
+        if (dbg && tid == 0) { dbg[2] = clock64(); dbg[8] = dbg_wait; }
         const int64_t trow = row0 + warp * 32 + lane;
         int64_t row = trow;
         if (p.perm) row = __ldg(p.perm + trow);
@@ -391,8 +399,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, NT) : make_idesc_tf32(TILE_M, NT);
         int s = 0;
         uint32_t ph = 0;
+        long long dbg_wait_full = 0;
         for (int it = 0; it < n_items; it++) {
-            mbar_wait(s_full + s, ph);
+            if (dbg && lane == 0) {
+                const long long t0 = clock64();
+                mbar_wait(s_full + s, ph);
+                dbg_wait_full += clock64() - t0;
+            } else {
+                mbar_wait(s_full + s, ph);
+            }
             tc_fence_after();
             proxy_fence_async();
             if (lane == 0) {
@@ -410,6 +425,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
+        if (dbg && lane == 0) dbg[9] = dbg_wait_full;
     }
     if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
@@ -1234,6 +1250,43 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     const size_t smem = stages * stage_bytes + fixed;
     // with a row permutation the tiles run over the (padded) table rows, destination rows come from perm
     dim3 grid((unsigned)u2_ceil_div(perm ? ld : n_dst, TILE_M), (unsigned)(Cd / NT));
+    static const int debug_timing = getenv("U2_DEBUG_CONV_TIMING") ? 1 : 0;
+    if (debug_timing) {  // per-CTA phase clocks: where does a work item's time go (synchronises; diagnostics only)
+        const size_t n_cta = (size_t)grid.x * grid.y;
+        long long *d_dbg = nullptr;
+        U2_CUDA_OK(cudaMalloc(&d_dbg, n_cta * 16 * sizeof(long long)));
+        U2_CUDA_OK(cudaMemsetAsync(d_dbg, 0, n_cta * 16 * sizeof(long long), st));
+        p.dbg = d_dbg;
+        int rc = bf16 ? (ROWB == 128 ? launch_fwd_v1<128, true>(p, grid, smem, st) : launch_fwd_v1<64, true>(p, grid, smem, st))
+                      : (ROWB == 128 ? launch_fwd_v1<128, false>(p, grid, smem, st) : launch_fwd_v1<64, false>(p, grid, smem, st));
+        if (rc) return rc;
+        U2_CUDA_OK(cudaStreamSynchronize(st));
+        long long *h = (long long *)malloc(n_cta * 16 * sizeof(long long));
+        U2_CUDA_OK(cudaMemcpy(h, d_dbg, n_cta * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+        double items = 0, main = 0, epi = 0, wait_e = 0, wait_f = 0, setup = 0;
+        long long t_min = 0x7FFFFFFFFFFFFFFFLL, t_max = 0;
+        size_t live = 0;
+        for (size_t i = 0; i < n_cta; i++) {
+            const long long *d = h + i * 16;
+            if (d[6] <= 0) continue;
+            live++;
+            items += (double)d[6];
+            setup += (double)(d[1] - d[0]);
+            main += (double)(d[2] - d[1]);   // producers: first gather issued .. last gather issued
+            epi += (double)(d[4] - d[2]);    // producers: wait for the accumulator + drain
+            wait_e += (double)d[8];
+            wait_f += (double)d[9];
+            if (d[0] < t_min) t_min = d[0];
+            if (d[5] > t_max) t_max = d[5];
+        }
+        fprintf(stderr, "[conv dbg] Cs=%d Cd=%d NT=%d rows=%lld ctas=%zu stages=%d | items/cta %.1f | per item: issue-span %.0f "
+                        "(producer waits empty %.0f, mma waits full %.0f) | setup %.0f  tail+epilogue %.0f cycles/cta\n",
+                Cs, Cd, NT, (long long)n_dst, live, stages, items / live, main / items, wait_e / items, wait_f / items,
+                setup / live, epi / live);
+        free(h);
+        cudaFree(d_dbg);
+        return 0;
+    }
     if (bf16) return ROWB == 128 ? launch_fwd_v1<128, true>(p, grid, smem, st) : launch_fwd_v1<64, true>(p, grid, smem, st);
     return ROWB == 128 ? launch_fwd_v1<128, false>(p, grid, smem, st) : launch_fwd_v1<64, false>(p, grid, smem, st);
 }
