@@ -35,6 +35,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -278,6 +281,42 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         int s = 0;
         uint32_t ph = 0;
         long long dbg_wait = 0;
+        if (p.cp_mode == 9) {
+            // Register-staged variant: LDG.128 -> STS.128 instead of LDGSTS (the LSU spends ~16 cycles per warp-level
+            // LDGSTS.128; plain loads + stores are cheaper per byte).  The loads of item i+1 are in flight while
+            // item i is stored, so two items of gathers per producer warp hide the L2 latency.
+            uint4 cur[CHUNKS], nxt[CHUNKS];
+            uint32_t m = kmask;
+            int cc = 0;
+            auto issue = [&](uint4 (&v)[CHUNKS], uint32_t mm, int c) {
+                const int k = __ffs(mm) - 1;
+                const int *tab_k = s_tab + k * TILE_M + tid / CHUNKS;
+                const uint8_t *xc = p.X + (size_t)c * ROWB + chunk * 16;
+#pragma unroll
+                for (int i = 0; i < CHUNKS; i++) {
+                    const int src = tab_k[i * ROWS_PER_IT];
+                    v[i] = src >= 0 ? __ldg(reinterpret_cast<const uint4 *>(xc + (size_t)src * (size_t)(p.Cs * ES)))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            if (n_items > 0) issue(nxt, m, 0);
+            for (int it = 0; it < n_items; it++) {
+#pragma unroll
+                for (int i = 0; i < CHUNKS; i++) cur[i] = nxt[i];
+                if (++cc == n_cc) { cc = 0; m &= m - 1; }
+                if (it + 1 < n_items) issue(nxt, m, cc);
+                mbar_wait(s_empty + s, ph ^ 1u);
+                const uint32_t a_dst = smem_u32(s_stage + (size_t)s * stage_bytes) + dst0;
+#pragma unroll
+                for (int i = 0; i < CHUNKS; i++)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_dst + i * (ROWS_PER_IT * 16)), "r"(cur[i].x),
+                                 "r"(cur[i].y), "r"(cur[i].z), "r"(cur[i].w)
+                                 : "memory");
+                proxy_fence_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(s_full + s);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+        } else
         for (uint32_t m = kmask; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
             const int *tab_k = s_tab + k * TILE_M + tid / CHUNKS;
