@@ -38,9 +38,9 @@ for n, c, mult in shapes:
     P = lambda a: a.data_ptr()
     r = {}
     r["stats"] = (t(lambda: _lib.check(L.u2_bn_stats(P(x), n, c, P(sums), P(scr), scr.numel(), st))), 4)
-    r["apply"] = (t(lambda: _lib.check(L.u2_bn_apply_dual(P(x), n, c, P(sums), 1e-5, 0.1, P(g), P(b), 1, P(y), P(yb), P(mean), P(inv), None, None, st))), 10)
-    r["bwd_reduce"] = (t(lambda: _lib.check(L.u2_bn_bwd_reduce(P(dy), P(x), n, c, P(mean), P(inv), P(g), P(b), 1, P(dsum), P(scr), scr.numel(), st))), 8)
-    r["bwd_apply"] = (t(lambda: _lib.check(L.u2_bn_bwd_apply_dual(P(dy), P(x), n, c, P(mean), P(inv), P(g), P(b), P(dsum), P(sums) + 16 * c, 1, None, P(yb), st))), 10)
+    r["apply"] = (t(lambda: _lib.check(L.u2_bn_apply_dual(P(x), n, c, P(sums), 1e-5, 0.1, P(g), P(b), 1, None, P(y), P(yb), P(mean), P(inv), None, None, st))), 10)
+    r["bwd_reduce"] = (t(lambda: _lib.check(L.u2_bn_bwd_reduce(P(dy), P(x), n, c, P(mean), P(inv), P(g), P(b), 1, None, P(dsum), P(scr), scr.numel(), st))), 8)
+    r["bwd_apply"] = (t(lambda: _lib.check(L.u2_bn_bwd_apply_dual(P(dy), P(x), n, c, P(mean), P(inv), P(g), P(b), P(dsum), P(sums) + 16 * c, 1, None, None, None, P(yb), st))), 10)
     line = f"n={n:6d} C={c:3d}:"
     for k, (ms, bpe) in r.items():
         gbs = n * c * bpe / ms / 1e6
