@@ -293,9 +293,14 @@ def test_spvcnn_fused_conv_bn_vs_unfused(tc):
             # counters are bumped once per forward by one multi-tensor add (fusion.optimize), not per layer
             assert all(int(v) == 1 for k, v in net.state_dict().items() if k.endswith("num_batches_tracked"))
             convs = [m for m in net.modules() if isinstance(m, gts.nn.Conv3d) and m.kernel.grad is not None]
+            # eval mode goes through the same fused module tree (absorbed BatchNorms, residual tails) with running stats
+            net.eval()
+            with torch.no_grad():
+                out_eval = net({"lidar": gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())})["x_vox"]
             outs.append((out.detach(), convs[5].kernel.grad.clone(), convs[-3].kernel.grad.clone(),
-                         {k: v.clone() for k, v in net.state_dict().items() if "running_var" in k}))
+                         {k: v.clone() for k, v in net.state_dict().items() if "running_var" in k}, out_eval))
         a, b = outs
+        assert rel_err(b[4], a[4]) < TF32_REL and not torch.equal(a[4], a[0])
         assert rel_err(b[0], a[0]) < TF32_REL
         assert rel_err(b[1], a[1]) < 0.2 and rel_err(b[2], a[2]) < 0.2  # sanity bound (see test_spvcnn_bf16_vs_oracle)
         for k in a[3]:
