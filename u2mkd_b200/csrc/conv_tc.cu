@@ -1223,6 +1223,26 @@ size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd
 template <int ROWB, bool BF16>
 static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_t st) {
     U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the launcher sizes the stages for 2-3 co-resident CTAs: ask for the full shared-memory carve-out, otherwise the
+    // driver may keep a larger L1 and fewer CTAs fit than planned
+    static const int carve = getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared;
+    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    if (getenv("U2_DEBUG_CONV_TIMING")) {
+        int nb = 0, nb0 = 0, nb32 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_fwd_tc_kernel<ROWB, BF16>, NUM_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, conv_fwd_tc_kernel<ROWB, BF16>, NUM_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb32, conv_fwd_tc_kernel<ROWB, BF16>, NUM_THREADS, 32768);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, conv_fwd_tc_kernel<ROWB, BF16>);
+        int smem_sm = 0, smem_blk = 0, regs_sm = 0;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, 0);
+        cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0);
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, 0);
+        fprintf(stderr, "[conv dbg] occupancy: %d CTAs/SM at %zu B dynamic smem (%d at 0 B, %d at 32 KB); regs %d, static smem %zu, "
+                        "local %zu, maxDyn %d, carveout %d; device: smem/SM %d, smem/block optin %d, regs/SM %d\n",
+                nb, smem, nb0, nb32, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes,
+                fa.preferredShmemCarveout, smem_sm, smem_blk, regs_sm);
+    }
     conv_fwd_tc_kernel<ROWB, BF16><<<grid, NUM_THREADS, smem, st>>>(p);
     U2_LAUNCH_OK();
     return 0;
@@ -1318,6 +1338,29 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
             if (d[0] < t_min) t_min = d[0];
             if (d[5] > t_max) t_max = d[5];
         }
+        {   // co-residency actually reached: CTAs of one SM share its clock64, so count overlapping lifetimes per SM
+            int max_conc = 0;
+            double busy = 0, area = 0;
+            for (int sm = 0; sm < 256; sm++) {
+                long long lo = 0x7FFFFFFFFFFFFFFFLL, hi = 0;
+                for (size_t i = 0; i < n_cta; i++) {
+                    const long long *d = h + i * 16;
+                    if (d[6] <= 0 || d[7] != sm) continue;
+                    if (d[0] < lo) lo = d[0];
+                    if (d[5] > hi) hi = d[5];
+                    area += (double)(d[5] - d[0]);
+                    int conc = 0;
+                    for (size_t j = 0; j < n_cta; j++) {
+                        const long long *e = h + j * 16;
+                        if (e[6] > 0 && e[7] == sm && e[0] <= d[0] && e[5] > d[0]) conc++;
+                    }
+                    if (conc > max_conc) max_conc = conc;
+                }
+                if (hi > lo) busy += (double)(hi - lo);
+            }
+            fprintf(stderr, "[conv dbg] co-resident CTAs per SM: max %d, average %.2f over the SMs' busy spans\n", max_conc,
+                    busy > 0 ? area / busy : 0.0);
+        }
         fprintf(stderr, "[conv dbg] Cs=%d Cd=%d NT=%d rows=%lld ctas=%zu stages=%d | items/cta %.1f | per item: issue-span %.0f "
                         "(producer waits empty %.0f, mma waits full %.0f) | setup %.0f  tail+epilogue %.0f cycles/cta\n",
                 Cs, Cd, NT, (long long)n_dst, live, stages, items / live, main / items, wait_e / items, wait_f / items,
@@ -1403,9 +1446,13 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     dim3 grid((unsigned)u2_ceil_div(n_rows, p.wg_pairs), (unsigned)K, (unsigned)(u2_ceil_div(p.n_mt, TM) * p.n_nt));
     if (bf16) {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared));
         conv_wgrad_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
     } else {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared));
         conv_wgrad_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(p);
     }
     U2_LAUNCH_OK();
