@@ -28,6 +28,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.u2_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every binding in _lib._SIGNATURES has as many arguments as its declaration in include/u2mkd.h and the
+    same kinds (pointer / 64-bit / 32-bit / float / size_t): a drifted binding corrupts the call silently."""
+    from u2mkd_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "u2mkd.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decls = {m.group(2): (m.group(1).strip(), m.group(3))
+             for m in re.finditer(r"^([A-Za-z_][A-Za-z0-9_ \*]*?)\b(u2_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.M | re.S)}
+    assert set(_lib._SIGNATURES) <= set(decls), set(_lib._SIGNATURES) - set(decls)
+
+    def kind(c_type):
+        t = " ".join(c_type.replace("const", " ").split())
+        if "*" in t or t.startswith("u2_stream_t"):
+            return "ptr"
+        return {"int64_t": "i64", "int32_t": "i32", "int": "i32", "float": "f32", "size_t": "size", "double": "f64"}[t]
+
+    ctk = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int64: "i64", ctypes.c_int32: "i32", ctypes.c_int: "i32",
+           ctypes.c_float: "f32", ctypes.c_size_t: "size", ctypes.c_double: "f64"}
+    for name, (restype, argtypes) in _lib._SIGNATURES.items():
+        ret, params = decls[name]
+        params = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]
+        want = [kind(re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", p).strip() or p) for p in params]
+        got = [ctk[a] for a in argtypes]
+        assert got == want, (name, got, want)
+        assert ctk.get(restype, "ptr") == kind(ret), (name, restype, ret)
+
+
 def test_surface_matches_reference_call_sites():
     """Every torchsparse name U2MKD imports exists with the expected shape."""
     import u2mkd_b200
