@@ -1003,10 +1003,14 @@ struct WgradParams {
     int64_t ld;
     int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt, cp_mode, TM;
     int wg_pairs;  // pairs per CTA, multiple of 128, <= WG_PAIRS
+    long long *dbg;  // optional per-CTA phase clocks (U2_DEBUG_CONV_TIMING)
+    int npw;         // producer warps: 4 (warps 0-3) or 8 (+ warps 6-9) when only one CTA fits an SM
 };
 
+constexpr int WG_MAX_THREADS = NUM_THREADS + 4 * 32;  // + 4 optional extra producer warps (warps 6-9)
+
 template <bool BF16>
-__global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const WgradParams p) {
     using G = WgGeom<BF16>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int NT = p.NT;
@@ -1025,17 +1029,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     const int k = blockIdx.y;
     const int mt = (blockIdx.z / p.n_nt) * p.TM, nt = blockIdx.z % p.n_nt;  // first input slice of this CTA
     // pair range of this CTA (all threads compute the same scalar prefix over <= 32 sizes)
-    int koff = 0;
-    for (int j = 0; j < k; j++) koff += __ldg(p.nbsizes + j);
+    int koff = (lane < k) ? __ldg(p.nbsizes + lane) : 0;  // K <= 32: one load per lane, then a warp sum
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) koff += __shfl_xor_sync(0xFFFFFFFFu, koff, o);
     const int n_k = __ldg(p.nbsizes + k);
     const int c0 = blockIdx.x * p.wg_pairs;
     if (c0 >= n_k) return;
     const int n_pairs = min(p.wg_pairs, n_k - c0);
     const int n_items = (n_pairs + G::KR - 1) / G::KR;
+    long long *dbg = p.dbg ? p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+    if (dbg && tid == 0) { dbg[0] = clock64(); dbg[6] = n_items; }
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) {
-            mbar_init(s_full + s, TILE_M);
+            mbar_init(s_full + s, p.npw * 32);
             mbar_init(s_empty + s, 1);
         }
         mbar_init(s_accum, 1);
@@ -1045,19 +1052,29 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
         tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
-    // (a-row, b-row) of every pair of the chunk; padded to a whole stage with -1
+    // (a-row, b-row) of every pair of the chunk; padded to a whole stage with -1.  Two dependent global loads per
+    // pair (flat index -> neighbour table): 8 pairs per thread are in flight at a time, otherwise this prologue is a
+    // chain of ~2 x 11 exposed L2 latencies (measured 20 k cycles per CTA before batching).
     {
         const int *flat = p.flat + koff + c0;
         const int padded = n_items * G::KR;
-        for (int pr = tid; pr < padded; pr += NUM_THREADS) {
-            int2 ab = make_int2(-1, -1);
-            if (pr < n_pairs) {
-                const int f = __ldg(flat + pr);
-                const int o = f - k * (int)p.ld;
-                const int i = __ldg(p.nbr + f);
-                ab = p.swap ? make_int2(o, i) : make_int2(i, o);
+        const int nthr = blockDim.x;
+        for (int pr0 = tid; pr0 < padded; pr0 += 8 * nthr) {
+            int f[8], in[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int pr = pr0 + u * nthr;
+                f[u] = pr < n_pairs ? __ldg(flat + pr) : -1;
             }
-            s_pairs[pr] = ab;
+#pragma unroll
+            for (int u = 0; u < 8; u++) in[u] = f[u] >= 0 ? __ldg(p.nbr + f[u]) : -1;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int pr = pr0 + u * nthr;
+                if (pr >= padded) break;
+                const int o = f[u] >= 0 ? f[u] - k * (int)p.ld : -1;
+                s_pairs[pr] = p.swap ? make_int2(o, in[u]) : make_int2(in[u], o);
+            }
         }
     }
     tc_fence_before();
@@ -1065,21 +1082,31 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     const int m0 = mt * TILE_M, n0 = nt * NT;
+    if (dbg && tid == 0) dbg[1] = clock64();
 
-    if (warp < 4) {
+    if (warp < 4 || warp >= 6) {
         // ============================ producers: gather both operands ============================
+        const int pw = warp < 4 ? warp : warp - 2;  // producer index 0 .. npw-1
+        const int npw = p.npw;
+        long long dbg_wait = 0;
         const int cc = lane & 7;     // 16-byte chunk inside a 128-byte atom row
         const int rsub = lane >> 3;  // pair inside a group of 4
         const size_t a_pitch = (size_t)p.Cs * G::ES, b_pitch = (size_t)p.Cd * G::ES;
         for (int it = 0; it < n_items; it++) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            mbar_wait(s_empty + s, ph ^ 1u);
+            if (dbg && tid == 0) {
+                const long long t0 = clock64();
+                mbar_wait(s_empty + s, ph ^ 1u);
+                dbg_wait += clock64() - t0;
+            } else {
+                mbar_wait(s_empty + s, ph ^ 1u);
+            }
             const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t b_base = a_base + A_BYTES;
             const int2 *pairs = s_pairs + it * G::KR;
             // A: units (input slice, channel atom, 32-row block) w, w+4, ...
-            for (int u = warp; u < TM * G::A_ATOMS * G::RB; u += 4) {
+            for (int u = pw; u < TM * G::A_ATOMS * G::RB; u += npw) {
                 const int a_atom = u / G::RB, a_rb = u % G::RB;  // a_atom counts atoms across the TM slices
                 const int a_ch = m0 + a_atom * G::CPA + cc * (16 / G::ES);
                 const bool a_ch_ok = a_ch < p.Cs;
@@ -1093,7 +1120,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
                 }
             }
             // B: units (channel atom, 32-row block) w, w+4, ...
-            for (int u = warp; u < n_batoms * G::RB; u += 4) {
+            for (int u = pw; u < n_batoms * G::RB; u += npw) {
                 const int atom = u / G::RB, rb = u % G::RB;
                 const int ch = atom * G::CPA + cc * (16 / G::ES);
                 const bool ch_ok = ch < NT;
@@ -1109,15 +1136,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
             cp_async_mbar_arrive_noinc(s_full + s);
         }
         // ============================ epilogue: reduce the tile into dW[k] ============================
+        if (dbg && tid == 0) { dbg[2] = clock64(); dbg[8] = dbg_wait; }
         mbar_wait(s_accum, 0);
         tc_fence_after();
+        // a warp may only touch TMEM lanes 32 * (warp % 4) ..; with 8 producer warps the second set takes the upper
+        // half of the columns
+        const int q = warp & 3, half = warp >= 6 ? 1 : 0, nh = npw / 4;
+        const int c_lo = (NT / 16 * half / nh) * 16, c_hi = (NT / 16 * (half + 1) / nh) * 16;
         for (int tm = 0; tm < TM; tm++) {
-            const int ci = m0 + tm * TILE_M + warp * 32 + lane;  // accumulator row (TMEM lane) = input channel
+            const int ci = m0 + tm * TILE_M + q * 32 + lane;  // accumulator row (TMEM lane) = input channel
             if (m0 + tm * TILE_M >= p.Cs) break;
             float *out = p.dW + ((int64_t)k * p.Cs + ci) * p.Cd + n0;
-            for (int c = 0; c < NT; c += 16) {
+            for (int c = c_lo; c < c_hi; c += 16) {
                 uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tm * NT + c), v);
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tm * NT + c), v);
                 tmem_ld_wait();
                 if (ci < p.Cs) {
 #pragma unroll
@@ -1131,10 +1163,17 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
     } else if (warp == 5) {
         // ============================ MMA issuer ============================
         const uint32_t idesc = make_idesc_mn(BF16, TILE_M, NT);
+        long long dbg_wait_full = 0;
         for (int it = 0; it < n_items; it++) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            mbar_wait(s_full + s, ph);
+            if (dbg && lane == 0) {
+                const long long t0 = clock64();
+                mbar_wait(s_full + s, ph);
+                dbg_wait_full += clock64() - t0;
+            } else {
+                mbar_wait(s_full + s, ph);
+            }
             tc_fence_after();
             proxy_fence_async();
             if (lane == 0) {
@@ -1154,10 +1193,13 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_wgrad_tc_kernel(const WgradP
             }
             __syncwarp();
         }
+        if (dbg && lane == 0) dbg[9] = dbg_wait_full;
     }
+    if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (dbg && tid == 160) { dbg[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
 }
 
 __device__ __forceinline__ unsigned int pack_bf16x2(float lo, float hi) {
@@ -1248,6 +1290,53 @@ static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_
     return 0;
 }
 
+// Host side of U2_DEBUG_CONV_TIMING: per-CTA clock64 stamps (16 slots per CTA) -> one summary line.
+// slots: 0 start, 1 setup done, 2 producers issued their last item, 4 epilogue done, 5 CTA end, 6 items, 7 SM id,
+//        8 producer cycles waiting for a free stage, 9 MMA-thread cycles waiting for data
+static void conv_dbg_report(const char *tag, const long long *d_dbg, size_t n_cta) {
+    long long *h = (long long *)malloc(n_cta * 16 * sizeof(long long));
+    if (cudaMemcpy(h, d_dbg, n_cta * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) { free(h); return; }
+    double items = 0, main = 0, epi = 0, wait_e = 0, wait_f = 0, setup = 0;
+    size_t live = 0;
+    for (size_t i = 0; i < n_cta; i++) {
+        const long long *d = h + i * 16;
+        if (d[6] <= 0) continue;
+        live++;
+        items += (double)d[6];
+        setup += (double)(d[1] - d[0]);
+        main += (double)(d[2] - d[1]);
+        epi += (double)(d[4] - d[2]);
+        wait_e += (double)d[8];
+        wait_f += (double)d[9];
+    }
+    // co-residency actually reached: CTAs of one SM share its clock64, so count overlapping lifetimes per SM
+    int max_conc = 0;
+    double busy = 0, area = 0;
+    for (int sm = 0; sm < 256; sm++) {
+        long long lo = 0x7FFFFFFFFFFFFFFFLL, hi = 0;
+        for (size_t i = 0; i < n_cta; i++) {
+            const long long *d = h + i * 16;
+            if (d[6] <= 0 || d[7] != sm) continue;
+            if (d[0] < lo) lo = d[0];
+            if (d[5] > hi) hi = d[5];
+            area += (double)(d[5] - d[0]);
+            int conc = 0;
+            for (size_t j = 0; j < n_cta; j++) {
+                const long long *e = h + j * 16;
+                if (e[6] > 0 && e[7] == sm && e[0] <= d[0] && e[5] > d[0]) conc++;
+            }
+            if (conc > max_conc) max_conc = conc;
+        }
+        if (hi > lo) busy += (double)(hi - lo);
+    }
+    if (live)
+        fprintf(stderr, "[conv dbg] %s ctas=%zu | items/cta %.1f | per item: issue-span %.0f (producer waits empty %.0f, mma waits "
+                        "full %.0f) | setup %.0f  tail+epilogue %.0f cycles/cta | co-resident CTAs/SM max %d avg %.2f\n",
+                tag, live, items / live, main / items, wait_e / items, wait_f / items, setup / live, epi / live, max_conc,
+                busy > 0 ? area / busy : 0.0);
+    free(h);
+}
+
 // X: fp32 rows (math TF32) or bf16 rows (math BF16); W always the fp32 parameter tensor.
 int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
@@ -1320,52 +1409,9 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
                       : (ROWB == 128 ? launch_fwd_v1<128, false>(p, grid, smem, st) : launch_fwd_v1<64, false>(p, grid, smem, st));
         if (rc) return rc;
         U2_CUDA_OK(cudaStreamSynchronize(st));
-        long long *h = (long long *)malloc(n_cta * 16 * sizeof(long long));
-        U2_CUDA_OK(cudaMemcpy(h, d_dbg, n_cta * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-        double items = 0, main = 0, epi = 0, wait_e = 0, wait_f = 0, setup = 0;
-        long long t_min = 0x7FFFFFFFFFFFFFFFLL, t_max = 0;
-        size_t live = 0;
-        for (size_t i = 0; i < n_cta; i++) {
-            const long long *d = h + i * 16;
-            if (d[6] <= 0) continue;
-            live++;
-            items += (double)d[6];
-            setup += (double)(d[1] - d[0]);
-            main += (double)(d[2] - d[1]);   // producers: first gather issued .. last gather issued
-            epi += (double)(d[4] - d[2]);    // producers: wait for the accumulator + drain
-            wait_e += (double)d[8];
-            wait_f += (double)d[9];
-            if (d[0] < t_min) t_min = d[0];
-            if (d[5] > t_max) t_max = d[5];
-        }
-        {   // co-residency actually reached: CTAs of one SM share its clock64, so count overlapping lifetimes per SM
-            int max_conc = 0;
-            double busy = 0, area = 0;
-            for (int sm = 0; sm < 256; sm++) {
-                long long lo = 0x7FFFFFFFFFFFFFFFLL, hi = 0;
-                for (size_t i = 0; i < n_cta; i++) {
-                    const long long *d = h + i * 16;
-                    if (d[6] <= 0 || d[7] != sm) continue;
-                    if (d[0] < lo) lo = d[0];
-                    if (d[5] > hi) hi = d[5];
-                    area += (double)(d[5] - d[0]);
-                    int conc = 0;
-                    for (size_t j = 0; j < n_cta; j++) {
-                        const long long *e = h + j * 16;
-                        if (e[6] > 0 && e[7] == sm && e[0] <= d[0] && e[5] > d[0]) conc++;
-                    }
-                    if (conc > max_conc) max_conc = conc;
-                }
-                if (hi > lo) busy += (double)(hi - lo);
-            }
-            fprintf(stderr, "[conv dbg] co-resident CTAs per SM: max %d, average %.2f over the SMs' busy spans\n", max_conc,
-                    busy > 0 ? area / busy : 0.0);
-        }
-        fprintf(stderr, "[conv dbg] Cs=%d Cd=%d NT=%d rows=%lld ctas=%zu stages=%d | items/cta %.1f | per item: issue-span %.0f "
-                        "(producer waits empty %.0f, mma waits full %.0f) | setup %.0f  tail+epilogue %.0f cycles/cta\n",
-                Cs, Cd, NT, (long long)n_dst, live, stages, items / live, main / items, wait_e / items, wait_f / items,
-                setup / live, epi / live);
-        free(h);
+        char tag[128];
+        snprintf(tag, sizeof tag, "fwd Cs=%d Cd=%d NT=%d rows=%lld stages=%d", Cs, Cd, NT, (long long)n_dst, stages);
+        conv_dbg_report(tag, d_dbg, n_cta);
         cudaFree(d_dbg);
         return 0;
     }
@@ -1442,20 +1488,41 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     U2_CHECK_ARG(stages >= 2, "u2_conv_wgrad_tc: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + fixed;
+    // One warp keeps issuing a 16-byte LDGSTS only every ~120 cycles; two co-resident CTAs (8 producer warps) come close
+    // to what the LSU takes, a lone CTA (wide layers: its accumulators fill TMEM) does not -> give it 8 producer warps.
+    static const int npw_env = getenv("U2_WGRAD_NPW") ? atoi(getenv("U2_WGRAD_NPW")) : 0;
+    const bool lone = 2 * cols > 512 || 2 * (smem + 1024) > budget;
+    p.npw = npw_env == 4 || npw_env == 8 ? npw_env : (lone ? 8 : 4);
+    const int threads = NUM_THREADS + (p.npw == 8 ? 4 * 32 : 0);
     // a single offset has at most n_rows pairs (one per row of the table's row side)
     dim3 grid((unsigned)u2_ceil_div(n_rows, p.wg_pairs), (unsigned)K, (unsigned)(u2_ceil_div(p.n_mt, TM) * p.n_nt));
+    p.dbg = nullptr;
+    static const int debug_timing = getenv("U2_DEBUG_CONV_TIMING") ? 1 : 0;
+    const size_t n_cta = (size_t)grid.x * grid.y * grid.z;
+    if (debug_timing) {
+        U2_CUDA_OK(cudaMalloc(&p.dbg, n_cta * 16 * sizeof(long long)));
+        U2_CUDA_OK(cudaMemsetAsync(p.dbg, 0, n_cta * 16 * sizeof(long long), st));
+    }
     if (bf16) {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared));
-        conv_wgrad_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
+        conv_wgrad_tc_kernel<true><<<grid, threads, smem, st>>>(p);
     } else {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared));
-        conv_wgrad_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(p);
+        conv_wgrad_tc_kernel<false><<<grid, threads, smem, st>>>(p);
     }
     U2_LAUNCH_OK();
+    if (debug_timing) {
+        U2_CUDA_OK(cudaStreamSynchronize(st));
+        char tag[160];
+        snprintf(tag, sizeof tag, "wgrad Cs=%d Cd=%d NT=%d TM=%d rows=%lld pairs/cta=%d stages=%d npw=%d", Cs, Cd, NT, TM,
+                 (long long)n_rows, p.wg_pairs, stages, p.npw);
+        conv_dbg_report(tag, p.dbg, n_cta);
+        cudaFree(p.dbg);
+    }
     return 0;
 }
 
