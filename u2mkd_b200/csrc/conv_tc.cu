@@ -1451,7 +1451,7 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
     // at `target` working CTAs, assuming ~40 % of the K * n_rows table entries are present; the price of smaller
     // chunks is one more fp32 reduction of the Cs x Cd tile into dW per chunk, hence the floor.
     static const int wg_fixed = getenv("U2_WGRAD_PAIRS") ? atoi(getenv("U2_WGRAD_PAIRS")) : 0;
-    static const int wg_min = getenv("U2_WGRAD_PAIRS_MIN") ? atoi(getenv("U2_WGRAD_PAIRS_MIN")) : 1024;
+    static const int wg_min = getenv("U2_WGRAD_PAIRS_MIN") ? atoi(getenv("U2_WGRAD_PAIRS_MIN")) : 2048;
     static const int wg_target = getenv("U2_WGRAD_TARGET_CTAS") ? atoi(getenv("U2_WGRAD_TARGET_CTAS")) : 8 * U2_NUM_SMS;
     {
         const int tm0 = (p.n_mt < 4 ? p.n_mt : 4);
