@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
 
 _MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
-_state = {"math": MATH_FP32, "sort_tiles": True, "multi_tile": False}
+_state = {"math": MATH_FP32, "sort_tiles": True, "multi_tile": False, "overlap_rows": 1 << 30}
 
 # instrumentation used by bench.py: number of kernels this library launched, and an optional
 # per-launch CUDA-event timer for the conv kernels (the dominant kernel of the path)
@@ -661,17 +661,51 @@ class ConvBNReLUFn(Function):
                                          None, dyb.data_ptr(), _st()))
         _count(3)
         grad_feats = grad_weight = None
-        if ctx.needs_input_grad[0]:
-            bwd_table = kmap.nbr if transposed else kmap.nbrT
-            grad_feats = _conv_gather_gemm("dgrad", kmap, dyb, weight, True, bwd_table, xb.shape[0], cin, MATH_BF16,
-                                           side=not transposed)
+        # dgrad and wgrad only share their inputs.  On the coarse strides neither fills the 148 SMs (a few hundred CTAs),
+        # so there wgrad runs on a side stream next to dgrad; the main stream waits for it before the gradients leave.
+        side = None
+        if (ctx.needs_input_grad[0] and ctx.needs_input_grad[2]
+                and 0 < _state.get("overlap_rows", 0) and n <= _state["overlap_rows"]):
+            side = _side_stream(dev)
+        tag = "+" if side is not None else ""  # conv timer: "+" = ran concurrently, the event time is not a solo duration
         if ctx.needs_input_grad[2]:
             grad_weight = torch.empty_like(weight)
             flat = kmap.flat_pairs
-            _timed("wgrad", kmap, n, K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
-                xb.data_ptr(), cin, dyb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
-                flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, _st())))
+
+            def wgrad():
+                _timed("wgrad" + tag, kmap, n, K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                    xb.data_ptr(), cin, dyb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
+                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, _st())))
+
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    wgrad()
+            else:
+                wgrad()
+        if ctx.needs_input_grad[0]:
+            bwd_table = kmap.nbr if transposed else kmap.nbrT
+            grad_feats = _conv_gather_gemm("dgrad" + tag, kmap, dyb, weight, True, bwd_table, xb.shape[0], cin, MATH_BF16,
+                                           side=not transposed)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
         return (grad_feats, None, grad_weight, dgamma, dbeta, dres) + (None,) * 8
+
+
+_side_streams = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key)
+    return _side_streams[key]
+
+
+def set_overlap_rows(rows: int) -> None:
+    """dgrad / wgrad of a fused conv layer run concurrently (two streams) when the layer has at most `rows` output
+    rows; 0 disables (default: every layer; measured 38.2 -> 37.0 ms per step)."""
+    _state["overlap_rows"] = int(rows)
 
 
 def _bn_group(bn):
