@@ -2,6 +2,8 @@ import sys, torch
 import os; sys.path.insert(0, os.environ.get("REPO", "/root/repo"))
 from oracle import ts_oracle
 from u2mkd_b200 import models, scans, torchsparse as ts
+if os.environ.get("THREADS"):
+    torch.set_num_threads(int(os.environ["THREADS"]))
 dev = torch.device("cuda:0")
 coords, feats = scans.make_batch([0], "nusc", 1, 0.2)
 torch.manual_seed(0)
