@@ -18,9 +18,9 @@ def oracle():
     import torch
     from oracle import ts_oracle
     ts_oracle.build()
-    # torch's CPU kernels give thread-count dependent whole-model gradients on 16-core hosts (2e-3 .. 9e-3 off at 1, 12
-    # and 16 intra-op threads, fp32 or fp64; exact to ~2e-6 at 4 and 8: scripts/smoke_repeat.py), so the
-    # checker runs with at most 8 threads
+    # torch's fp32 CPU kernels give thread-count dependent whole-model gradients (2e-3 .. 9e-3 from the fp64 result at
+    # 1, 3, 12 or 16 intra-op threads, ~5e-6 at 4-8: scripts/smoke_repeat.py), so the checker runs with
+    # at most 8 threads
     torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
     return ts_oracle
 
