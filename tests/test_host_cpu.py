@@ -153,6 +153,14 @@ def test_reference_model_files_import_on_the_product_surface():
         mine = models.product().SPVCNN(cr=0.5, pres=0.1, vres=0.1, num_classes=17)
         assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
         assert all(ref.state_dict()[k].shape == mine.state_dict()[k].shape for k in ref.state_dict())
+        # the fusion pass recognises the reference's own blocks (core/models/build_blocks.py:21-84) the same way
+        from u2mkd_b200 import fusion
+        fusion.optimize(ref)
+        fusion.optimize(mine)
+        count = lambda net: (sum(1 for m in net.modules() if getattr(m, "_u2_epilogue", None) is not None),
+                             sum(1 for m in net.modules() if type(m).__name__ == "ResidualBlock" and "forward" in m.__dict__))
+        assert count(ref) == count(mine) and count(ref)[0] >= 40 and count(ref)[1] >= 16
+        assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
     finally:
         sys.path.remove("/root/reference")
         for m in [m for m in sys.modules if m == "core" or m.startswith("core.")]:
@@ -167,3 +175,37 @@ def test_scan_generator_contract():
     assert np.unique(c, axis=0).shape[0] == c.shape[0]  # one point per voxel
     c2, _ = scans.make_batch([3, 4], "nusc", 1, 0.2)
     assert np.array_equal(c, c2)  # seeded
+
+
+def test_fusion_pass_structure_and_state_dict():
+    """fusion.optimize() rewires execution only: same module tree, parameter names and state_dict; every
+    Sequential(Conv3d, BatchNorm[, ReLU]) gets a conv epilogue, every ResidualBlock tail is folded, and calling it
+    twice changes nothing (core/models/build_blocks.py:21-84 is the pattern source)."""
+    from u2mkd_b200 import fusion, models
+    import u2mkd_b200.torchsparse as gts
+    torch.manual_seed(0)
+    net = models.product().SPVCNN(cr=0.5, pres=0.1, vres=0.1)
+    keys = list(net.state_dict().keys())
+    names = [n for n, _ in net.named_modules()]
+    fusion.optimize(net)
+    fusion.optimize(net)
+    assert list(net.state_dict().keys()) == keys and [n for n, _ in net.named_modules()] == names
+    convs = [m for m in net.modules() if isinstance(m, gts.nn.Conv3d)]
+    fused = [m for m in convs if getattr(m, "_u2_epilogue", None) is not None]
+    # every sparse conv of SPVCNN sits in front of a BatchNorm
+    assert len(fused) == len(convs) >= 40
+    for m in fused:
+        bn, relu = m._u2_epilogue
+        assert isinstance(bn, torch.nn.BatchNorm1d) and bn._u2_absorbed and isinstance(relu, bool)
+        assert bn not in list(m.children())  # the tuple keeps the BatchNorm out of the conv's own submodules
+    blocks = [m for m in net.modules() if type(m).__name__ == "ResidualBlock"]
+    assert len(blocks) >= 16 and all("forward" in b.__dict__ for b in blocks)
+    # the last conv of a block is fused WITHOUT its own ReLU: the block's ReLU comes after the residual add
+    assert all(list(b.net.children())[-2]._u2_epilogue[1] is False for b in blocks)
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+    assert all(getattr(m, "_u2_lazy_counter", False) for m in bns)
+    # turning the passes off leaves plain modules
+    net2 = models.product().SPVCNN(cr=0.5, pres=0.1, vres=0.1)
+    fusion.optimize(net2, fuse_conv_bn=False)
+    assert not any(getattr(m, "_u2_epilogue", None) for m in net2.modules())
+    assert not any("forward" in m.__dict__ for m in net2.modules() if type(m).__name__ == "ResidualBlock")
