@@ -209,3 +209,35 @@ def test_fusion_pass_structure_and_state_dict():
     fusion.optimize(net2, fuse_conv_bn=False)
     assert not any(getattr(m, "_u2_epilogue", None) for m in net2.modules())
     assert not any("forward" in m.__dict__ for m in net2.modules() if type(m).__name__ == "ResidualBlock")
+
+
+def test_fused_relu_survives_non_2d_input():
+    """fusion.optimize folds a ReLU into the preceding BatchNorm; for [N, C, H, W] input (BatchNorm2d converted to
+    SyncBatchNorm, core/models/fusion_blocks.py:101-103 + train_lc_nusc_tsd_full.py:80) the module falls back to torch's
+    kernels and must still apply that ReLU."""
+    from u2mkd_b200 import fusion
+    seq = torch.nn.Sequential(torch.nn.SyncBatchNorm(8), torch.nn.ReLU())
+    seq.eval()
+    with torch.no_grad():
+        seq[0].running_mean.uniform_(-1, 1)
+        seq[0].running_var.uniform_(0.5, 2)
+        x = torch.randn(2, 8, 5, 5)
+        want = seq(x)
+        fusion.optimize(seq)
+        got = seq(x)
+    assert float(want.min()) == 0.0 and torch.equal(got, want)
+
+
+def test_batch_norm_fallback_counts_batches_and_honours_momentum_none():
+    """The torch fallback of ops.batch_norm_relu (CPU here; on the GPU: C % 4 != 0, no affine) behaves like
+    nn.BatchNorm1d.forward: num_batches_tracked advances and momentum=None means the cumulative average."""
+    from u2mkd_b200 import ops
+    torch.manual_seed(0)
+    for momentum in (0.1, None):
+        a, b = torch.nn.BatchNorm1d(9, momentum=momentum), torch.nn.BatchNorm1d(9, momentum=momentum)
+        for step in range(3):
+            x = torch.randn(50, 9) * (step + 1) + step
+            ya, yb = a(x), ops.batch_norm_relu(x, b, relu=False)
+            assert torch.allclose(ya, yb, atol=1e-6)
+        assert int(b.num_batches_tracked) == 3
+        assert torch.allclose(a.running_mean, b.running_mean, atol=1e-6) and torch.allclose(a.running_var, b.running_var, atol=1e-5)

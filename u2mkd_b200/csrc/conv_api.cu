@@ -15,13 +15,6 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
                    void *scratch, size_t scratch_bytes, float *tile_stats, cudaStream_t st);
 int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
-int u2_conv_fwd_mt(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
-                   const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
-                   void *scratch, size_t scratch_bytes, cudaStream_t st);
-int u2_conv_fwd_tma_supported(int32_t Cs, int32_t Cd, int32_t K);
-int u2_conv_fwd_tma(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
-                    const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
-                    void *scratch, size_t scratch_bytes, cudaStream_t st);
 int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
                      int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
                      cudaStream_t st);
@@ -117,16 +110,7 @@ extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const
     U2_CHECK_ARG(perm != nullptr, "u2_conv_fwd_perm: null perm");
     U2_CHECK_ARG((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math),
                  "u2_conv_fwd_perm: unsupported shape/math");
-    if (math == U2_MATH_BF16)
-        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
-                              nullptr, (cudaStream_t)stream);
-    static const int use_tma = getenv("U2_NO_TMA_GATHER") ? 0 : 1;
-    if (tile_mask && use_tma && u2_conv_fwd_tma_supported(Cs, Cd, K))
-        return u2_conv_fwd_tma(X, n_src, Cs, W, w_transposed, tableP, perm, tile_mask, ld, n_dst, K, Cd, Y, scratch,
-                               scratch_bytes, (cudaStream_t)stream);
-    if (tile_mask)
-        return u2_conv_fwd_mt(X, n_src, Cs, W, w_transposed, tableP, perm, tile_mask, ld, n_dst, K, Cd, Y, scratch,
-                              scratch_bytes, (cudaStream_t)stream);
+    (void)tile_mask;
     return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
                           nullptr, (cudaStream_t)stream);
 #else

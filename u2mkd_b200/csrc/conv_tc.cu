@@ -166,6 +166,7 @@ struct FwdParams {
     long long *dbg;  // optional per-CTA phase timestamps (U2_DEBUG_CONV_TIMING)
     int cp_mode;
     float *tile_stats;  // optional [tiles * 4][2][Cd]: per-warp column sums / sums of squares of Y (fused BatchNorm)
+    int diag;  // U2_CONV_DIAG (timing diagnostics, results invalid): 1 = no weight loads, 2 = no gathers, 4 = gathers hit 128 hot rows
 };
 
 // Column sums over the 32 rows a warp holds (lane = row, r[j] = column j): a transposing butterfly, 31 shuffles
@@ -326,6 +327,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             for (int i = 0; i < CHUNKS; i++) {
                 const int src = tab_k[i * ROWS_PER_IT];
                 off[i] = src >= 0 ? (uint32_t)src * (uint32_t)(p.Cs * ES) + (uint32_t)(chunk * 16) : 0xFFFFFFFFu;  // bytes
+                if (p.diag & 4)
+                    off[i] = (uint32_t)(tid / CHUNKS + i * ROWS_PER_IT) * (uint32_t)(p.Cs * ES) + (uint32_t)(chunk * 16);
             }
             const uint8_t *xc = p.X;
             for (int cc = 0; cc < n_cc; cc++, xc += ROWB) {
@@ -340,7 +343,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
 #pragma unroll
                 for (int i = 0; i < CHUNKS; i++) {
                     const bool ok = off[i] != 0xFFFFFFFFu;
-                    cp_async16_mode(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u, p.cp_mode);
+                    if (!(p.diag & 2))
+                        cp_async16_mode(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u, p.cp_mode);
                 }
                 cp_async_mbar_arrive_noinc(s_full + s);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -427,8 +431,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                     mbar_wait(s_empty + s, ph ^ 1u);
                     const uint32_t b_base = smem_u32(s_stage + (size_t)s * stage_bytes + A_BYTES);
                     const uint8_t *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(ROWB * NT);
-                    mbar_arrive_expect_tx(s_full + s, (uint32_t)B_BYTES);
-                    bulk_g2s(b_base, blob, (uint32_t)B_BYTES, s_full + s);
+                    if (p.diag & 1) {
+                        mbar_arrive(s_full + s);
+                    } else {
+                        mbar_arrive_expect_tx(s_full + s, (uint32_t)B_BYTES);
+                        bulk_g2s(b_base, blob, (uint32_t)B_BYTES, s_full + s);
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -473,460 +481,6 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     if (dbg && tid == 160) { dbg[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
 }
 
-// ------------------------------------------------------------------ fwd / dgrad, multi-tile CTA
-// The single-tile kernel above is L2-bound on WEIGHT traffic: every (tile, offset, slice) item
-// streams a KC x NT weight blob (8-32 KB) next to <= 16 KB of gathered rows.  Here one CTA owns
-// T consecutive (mask-sorted) 128-row tiles with T accumulators side by side in TMEM and walks
-// offset -> channel slice -> tile, so a weight blob is fetched once per (offset, slice) and
-// reused by up to T tiles.  Gathered rows (A ring) and weight blobs (B ring) have their own
-// mbarrier pipelines.  Neighbour-table entries are read straight from global memory one offset
-// ahead (no shared-memory copy of the table); the per-tile offset masks come precomputed from
-// u2_kmap_sort_rows.
-constexpr int MAX_SA = 8, MAX_SB = 4;
-
-struct MtParams {
-    const float *X;
-    const float *Wt;
-    const int *table;
-    const int *perm;
-    const uint32_t *tile_mask;
-    float *Y;
-    int64_t ld, n_dst;
-    int Cs, Cd, K, NT, sa, sb, tmem_cols;
-};
-
-template <int KC, int T, int NPW>
-__global__ void __launch_bounds__((NPW + 2) * 32) conv_fwd_mt_kernel(const MtParams p) {
-    constexpr int CHUNKS = KC / 4;
-    constexpr int PT = NPW * 32;                 // producer threads
-    constexpr int ROWS_PER_IT = PT / CHUNKS;     // rows covered by one cp.async round of the producers
-    constexpr int PPT = TILE_M * CHUNKS / PT;    // 16-byte pieces per producer thread per item
-    static_assert(PPT >= 1 && TILE_M % ROWS_PER_IT == 0, "bad producer geometry");
-    constexpr int A_BYTES = CHUNKS * A_LBO;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int NT = p.NT;
-    const int B_LBO = NT * 16;
-    const int B_BYTES = CHUNKS * B_LBO;
-    uint8_t *s_a = smem;
-    uint8_t *s_b = smem + (size_t)p.sa * A_BYTES;
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(s_b + (size_t)p.sb * B_BYTES);
-    uint64_t *a_empty = a_full + MAX_SA;
-    uint64_t *b_full = a_empty + MAX_SA;
-    uint64_t *b_empty = b_full + MAX_SB;
-    uint64_t *s_accum = b_empty + MAX_SB;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_accum + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t tile0 = (int64_t)blockIdx.x * T;
-    const int64_t n_tiles = p.ld / TILE_M;
-    const int nt = blockIdx.y;
-    const int n_cc = p.Cs / KC;
-    const int n_nt = p.Cd / NT;
-
-    uint32_t tm[T];
-    uint32_t U = 0;
-#pragma unroll
-    for (int t = 0; t < T; t++) {
-        tm[t] = tile0 + t < n_tiles ? __ldg(p.tile_mask + tile0 + t) : 0u;
-        U |= tm[t];
-    }
-
-    if (tid == 0) {
-        for (int s = 0; s < p.sa; s++) {
-            mbar_init(a_full + s, PT);
-            mbar_init(a_empty + s, 1);
-        }
-        for (int s = 0; s < p.sb; s++) {
-            mbar_init(b_full + s, 1);
-            mbar_init(b_empty + s, 1);
-        }
-        mbar_init(s_accum, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == NPW + 1) {
-        tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
-
-    if (warp < NPW) {
-        // ============================ A producers ============================
-        const int chunk = tid % CHUNKS;
-        const int rsel = tid / CHUNKS;
-        const uint32_t dst0 = (uint32_t)(chunk * A_LBO + rsel * 16);
-        const int *tab0 = p.table + tile0 * TILE_M + rsel;
-        int s = 0;
-        uint32_t ph = 0;
-        int nxt[T][PPT];
-        auto fetch = [&](int k) {
-#pragma unroll
-            for (int t = 0; t < T; t++)
-#pragma unroll
-                for (int i = 0; i < PPT; i++)
-                    nxt[t][i] = (tm[t] >> k) & 1u ? __ldg(tab0 + (int64_t)k * p.ld + t * TILE_M + i * ROWS_PER_IT) : -1;
-        };
-        uint32_t m = U;
-        if (m) fetch(__ffs(m) - 1);
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t off[T][PPT];
-#pragma unroll
-            for (int t = 0; t < T; t++)
-#pragma unroll
-                for (int i = 0; i < PPT; i++)
-                    off[t][i] = nxt[t][i] >= 0 ? (uint32_t)nxt[t][i] * (uint32_t)p.Cs + (uint32_t)(chunk * 4) : 0xFFFFFFFFu;
-            if (m) fetch(__ffs(m) - 1);  // next offset's entries travel while this offset's rows are issued
-            const float *xc = p.X;
-            for (int cc = 0; cc < n_cc; cc++, xc += KC) {
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    if (!((tm[t] >> k) & 1u)) continue;
-                    mbar_wait(a_empty + s, ph ^ 1u);
-                    const uint32_t a_dst = smem_u32(s_a + (size_t)s * A_BYTES) + dst0;
-#pragma unroll
-                    for (int i = 0; i < PPT; i++) {
-                        const bool ok = off[t][i] != 0xFFFFFFFFu;
-                        cp_async16(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[t][i] : 0u), ok ? 16u : 0u);
-                    }
-                    cp_async_mbar_arrive_noinc(a_full + s);
-                    if (++s == p.sa) { s = 0; ph ^= 1u; }
-                }
-            }
-        }
-        // ============================ epilogue ============================
-        if (U) {
-            mbar_wait(s_accum, 0);
-            tc_fence_after();
-        }
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            if (tile0 + t >= n_tiles) break;
-            // warp w drains TMEM lanes 32*(w%4).. and the (w/4)-th slice of the NT columns
-            const int q = warp & 3, slice = warp >> 2;
-            constexpr int NSL = NPW / 4;
-            const int c_lo = (NT / 16 * slice / NSL) * 16, c_hi = (NT / 16 * (slice + 1) / NSL) * 16;
-            const int64_t trow = (tile0 + t) * TILE_M + q * 32 + lane;
-            const int64_t row = p.perm ? (int64_t)__ldg(p.perm + trow) : trow;
-            const bool live = row >= 0 && row < p.n_dst;
-            float *yrow = p.Y + (live ? row : 0) * p.Cd + nt * NT;
-            if (tm[t]) {
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT);
-                int c0 = c_lo;
-                for (; c0 + 64 <= c_hi; c0 += 64) {
-                    uint32_t v0[16], v1[16], v2[16], v3[16];
-                    tmem_ld16(t_row + (uint32_t)c0, v0);
-                    tmem_ld16(t_row + (uint32_t)c0 + 16, v1);
-                    tmem_ld16(t_row + (uint32_t)c0 + 32, v2);
-                    tmem_ld16(t_row + (uint32_t)c0 + 48, v3);
-                    tmem_ld_wait();
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + 32 + j) = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + 48 + j) = make_uint4(v3[j], v3[j + 1], v3[j + 2], v3[j + 3]);
-                        }
-                    }
-                }
-                for (; c0 < c_hi; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(t_row + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                }
-            } else if (live) {
-                for (int c0 = c_lo; c0 < c_hi; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-    } else if (warp == NPW) {
-        // ============================ B producer ============================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (uint32_t m = U; m; m &= m - 1) {
-                const int k = __ffs(m) - 1;
-                for (int cc = 0; cc < n_cc; cc++) {
-                    mbar_wait(b_empty + s, ph ^ 1u);
-                    const float *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(KC * NT);
-                    mbar_arrive_expect_tx(b_full + s, (uint32_t)B_BYTES);
-                    bulk_g2s(smem_u32(s_b + (size_t)s * B_BYTES), blob, (uint32_t)B_BYTES, b_full + s);
-                    if (++s == p.sb) { s = 0; ph ^= 1u; }
-                }
-            }
-        }
-    } else {
-        // ============================ MMA issuer ============================
-        const uint32_t idesc = make_idesc_tf32(TILE_M, NT);
-        int sa = 0, sb = 0;
-        uint32_t pha = 0, phb = 0, started = 0;
-        for (uint32_t m = U; m; m &= m - 1) {
-            const int k = __ffs(m) - 1;
-            for (int cc = 0; cc < n_cc; cc++) {
-                mbar_wait(b_full + sb, phb);
-                const uint32_t b_base = smem_u32(s_b + (size_t)sb * B_BYTES);
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    if (!((tm[t] >> k) & 1u)) continue;
-                    mbar_wait(a_full + sa, pha);
-                    tc_fence_after();
-                    proxy_fence_async();
-                    if (lane == 0) {
-                        const uint32_t a_base = smem_u32(s_a + (size_t)sa * A_BYTES);
-#pragma unroll
-                        for (int kk = 0; kk < KC / 8; kk++) {
-                            const uint64_t ad = make_smem_desc(a_base + kk * 2 * A_LBO, A_LBO, 128);
-                            const uint64_t bd = make_smem_desc(b_base + kk * 2 * B_LBO, B_LBO, 128);
-                            umma_tf32(tmem_base + (uint32_t)(t * NT), ad, bd, idesc, (((started >> t) & 1u) || kk > 0) ? 1u : 0u);
-                        }
-                        umma_commit(a_empty + sa);
-                    }
-                    __syncwarp();
-                    started |= 1u << t;
-                    if (++sa == p.sa) { sa = 0; pha ^= 1u; }
-                }
-                if (lane == 0) umma_commit(b_empty + sb);
-                __syncwarp();
-                if (++sb == p.sb) { sb = 0; phb ^= 1u; }
-            }
-        }
-        if (U && lane == 0) umma_commit(s_accum);
-        __syncwarp();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// ------------------------------------------------------------------ fwd / dgrad, TMA row gathers
-// The cp.async (LDGSTS) gather path tops out near 27 B/clk/SM: every item costs 32 warp-wide
-// LDGSTS.128 whatever the pipeline depth (measured: ~1200 cycles/item with 4 or 8 stages, L2 and
-// tensor pipes both < 50 % busy).  Here the rows are fetched by the TMA unit instead:
-// cp.async.bulk.tensor.2d.tile::gather4 takes FOUR row indices and lands their KC-wide slices as
-// four consecutive 128-byte rows of the canonical K-major SWIZZLE_128B UMMA layout; a missing
-// neighbour (-1) is an out-of-bounds coordinate, which the TMA zero-fills.  One warp issues the
-// 32 gather4 of a 128-row tile (one per lane, indices read as one int4 per lane straight from the
-// neighbour table, one offset ahead); the four former gather warps only run the epilogue.
-// Multi-tile as above: T accumulators in TMEM share every weight blob.
-struct TmaParams {
-    const float *Wt;
-    const int *table;
-    const int *perm;
-    const uint32_t *tile_mask;
-    float *Y;
-    int64_t ld, n_dst;
-    int Cs, Cd, K, NT, sa, sb, tmem_cols;
-};
-
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tmap, int col, int4 rows, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(col), "r"(rows.x), "r"(rows.y),
-        "r"(rows.z), "r"(rows.w)
-        : "memory");
-}
-
-// K-major SWIZZLE_128B descriptor: 8-row x 128-byte atoms, SBO = 1024 between atoms, LBO unused (=1)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
-    return make_smem_desc(saddr, 16, 1024) | ((uint64_t)2 << 61);
-}
-
-template <int T>
-__global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmapX, const TmaParams p) {
-    constexpr int KC = 32;
-    constexpr int A_BYTES = TILE_M * KC * 4;  // 16 KB, 16 swizzle atoms
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int NT = p.NT;
-    const int B_LBO = NT * 16;
-    const int B_BYTES = (KC / 4) * B_LBO;
-    uint8_t *s_a = smem;
-    uint8_t *s_b = smem + (size_t)p.sa * A_BYTES;
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(s_b + (size_t)p.sb * B_BYTES);
-    uint64_t *a_empty = a_full + MAX_SA;
-    uint64_t *b_full = a_empty + MAX_SA;
-    uint64_t *b_empty = b_full + MAX_SB;
-    uint64_t *s_accum = b_empty + MAX_SB;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_accum + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t tile0 = (int64_t)blockIdx.x * T;
-    const int64_t n_tiles = p.ld / TILE_M;
-    const int nt = blockIdx.y;
-    const int n_cc = p.Cs / KC;
-    const int n_nt = p.Cd / NT;
-
-    uint32_t tm[T];
-    uint32_t U = 0;
-#pragma unroll
-    for (int t = 0; t < T; t++) {
-        tm[t] = tile0 + t < n_tiles ? __ldg(p.tile_mask + tile0 + t) : 0u;
-        U |= tm[t];
-    }
-
-    if (tid == 0) {
-        for (int s = 0; s < p.sa; s++) {
-            mbar_init(a_full + s, 1);
-            mbar_init(a_empty + s, 1);
-        }
-        for (int s = 0; s < p.sb; s++) {
-            mbar_init(b_full + s, 1);
-            mbar_init(b_empty + s, 1);
-        }
-        mbar_init(s_accum, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapX)) : "memory");
-    if (warp == 5) {
-        tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
-
-    if (warp == 4) {
-        // ============================ producer: TMA gathers + weight blobs ============================
-        const int *tab0 = p.table + tile0 * TILE_M + 4 * lane;
-        int sa = 0, sb = 0;
-        uint32_t pha = 0, phb = 0;
-        int4 nxt[T];
-        auto fetch = [&](int k) {
-#pragma unroll
-            for (int t = 0; t < T; t++)
-                nxt[t] = (tm[t] >> k) & 1u ? __ldg(reinterpret_cast<const int4 *>(tab0 + (int64_t)k * p.ld + t * TILE_M))
-                                           : make_int4(-1, -1, -1, -1);
-        };
-        uint32_t m = U;
-        if (m) fetch(__ffs(m) - 1);
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            int4 cur[T];
-#pragma unroll
-            for (int t = 0; t < T; t++) cur[t] = nxt[t];
-            if (m) fetch(__ffs(m) - 1);
-            for (int cc = 0; cc < n_cc; cc++) {
-                if (lane == 0) {
-                    mbar_wait(b_empty + sb, phb ^ 1u);
-                    const float *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(KC * NT);
-                    mbar_arrive_expect_tx(b_full + sb, (uint32_t)B_BYTES);
-                    bulk_g2s(smem_u32(s_b + (size_t)sb * B_BYTES), blob, (uint32_t)B_BYTES, b_full + sb);
-                }
-                if (++sb == p.sb) { sb = 0; phb ^= 1u; }
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    if (!((tm[t] >> k) & 1u)) continue;
-                    if (lane == 0) {
-                        mbar_wait(a_empty + sa, pha ^ 1u);
-                        mbar_arrive_expect_tx(a_full + sa, (uint32_t)A_BYTES);
-                    }
-                    __syncwarp();
-                    tma_gather4(smem_u32(s_a + (size_t)sa * A_BYTES) + (uint32_t)lane * 512u, &tmapX, cc * KC, cur[t], a_full + sa);
-                    if (++sa == p.sa) { sa = 0; pha ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 5) {
-        // ============================ MMA issuer ============================
-        const uint32_t idesc = make_idesc_tf32(TILE_M, NT);
-        int sa = 0, sb = 0;
-        uint32_t pha = 0, phb = 0, started = 0;
-        for (uint32_t m = U; m; m &= m - 1) {
-            const int k = __ffs(m) - 1;
-            for (int cc = 0; cc < n_cc; cc++) {
-                mbar_wait(b_full + sb, phb);
-                const uint32_t b_base = smem_u32(s_b + (size_t)sb * B_BYTES);
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    if (!((tm[t] >> k) & 1u)) continue;
-                    mbar_wait(a_full + sa, pha);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_base = smem_u32(s_a + (size_t)sa * A_BYTES);
-#pragma unroll
-                        for (int kk = 0; kk < KC / 8; kk++) {
-                            const uint64_t ad = make_smem_desc_sw128(a_base + kk * 32);
-                            const uint64_t bd = make_smem_desc(b_base + kk * 2 * B_LBO, B_LBO, 128);
-                            umma_tf32(tmem_base + (uint32_t)(t * NT), ad, bd, idesc, (((started >> t) & 1u) || kk > 0) ? 1u : 0u);
-                        }
-                        umma_commit(a_empty + sa);
-                    }
-                    __syncwarp();
-                    started |= 1u << t;
-                    if (++sa == p.sa) { sa = 0; pha ^= 1u; }
-                }
-                if (lane == 0) umma_commit(b_empty + sb);
-                __syncwarp();
-                if (++sb == p.sb) { sb = 0; phb ^= 1u; }
-            }
-        }
-        if (U && lane == 0) umma_commit(s_accum);
-        __syncwarp();
-    } else {
-        // ============================ epilogue (warps 0-3) ============================
-        if (U) {
-            mbar_wait(s_accum, 0);
-            tc_fence_after();
-        }
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            if (tile0 + t >= n_tiles) break;
-            const int64_t trow = (tile0 + t) * TILE_M + warp * 32 + lane;
-            const int64_t row = p.perm ? (int64_t)__ldg(p.perm + trow) : trow;
-            const bool live = row >= 0 && row < p.n_dst;
-            float *yrow = p.Y + (live ? row : 0) * p.Cd + nt * NT;
-            if (tm[t]) {
-                const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NT);
-                int c0 = 0;
-                for (; c0 + 64 <= NT; c0 += 64) {
-                    uint32_t v0[16], v1[16], v2[16], v3[16];
-                    tmem_ld16(t_row + (uint32_t)c0, v0);
-                    tmem_ld16(t_row + (uint32_t)c0 + 16, v1);
-                    tmem_ld16(t_row + (uint32_t)c0 + 32, v2);
-                    tmem_ld16(t_row + (uint32_t)c0 + 48, v3);
-                    tmem_ld_wait();
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + 32 + j) = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + 48 + j) = make_uint4(v3[j], v3[j + 1], v3[j + 2], v3[j + 3]);
-                        }
-                    }
-                }
-                for (; c0 < NT; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(t_row + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                }
-            } else if (live) {
-                for (int c0 = 0; c0 < NT; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// W [K][Cs][Cd] (or [K][Cd][Cs] if WT) -> blobs [k][cc][nt][chunk][n][4] in UMMA K-major layout
 template <bool WT>
 __global__ void __launch_bounds__(256) pretile_weights_kernel(const float *__restrict__ W, float4 *__restrict__ out, int K,
                                                               int Cs, int Cd, int KC, int NT) {
@@ -1374,6 +928,8 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     p.tile_stats = tile_stats;
     static const int cp_mode = getenv("U2_CPASYNC_MODE") ? atoi(getenv("U2_CPASYNC_MODE")) : 1;  // .ca measured 15-25 % faster
     p.cp_mode = cp_mode;
+    const char *diag_env = getenv("U2_CONV_DIAG");  // read per call: scripts/diag_conv.py flips it between launches
+    p.diag = diag_env ? atoi(diag_env) : 0;
     p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
     int cols = 32;
     while (cols < NT) cols <<= 1;
@@ -1524,161 +1080,4 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
         cudaFree(p.dbg);
     }
     return 0;
-}
-
-template <int KC, int T, int NPW>
-static int launch_mt2(const MtParams &p, dim3 grid, size_t smem, cudaStream_t st) {
-    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_mt_kernel<KC, T, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_fwd_mt_kernel<KC, T, NPW><<<grid, (NPW + 2) * 32, smem, st>>>(p);
-    U2_LAUNCH_OK();
-    return 0;
-}
-template <int KC, int T>
-static int launch_mt(const MtParams &p, dim3 grid, size_t smem, cudaStream_t st) {
-    static const int npw = getenv("U2_CONV_NPW") ? atoi(getenv("U2_CONV_NPW")) : 8;
-    if (npw >= 16) return launch_mt2<KC, T, 16>(p, grid, smem, st);
-    if (npw >= 8) return launch_mt2<KC, T, 8>(p, grid, smem, st);
-    return launch_mt2<KC, T, 4>(p, grid, smem, st);
-}
-
-int u2_conv_fwd_mt(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
-                   const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
-                   void *scratch, size_t scratch_bytes, cudaStream_t st) {
-    U2_CHECK_ARG(n_src * (int64_t)Cs < 0xFFFFFFFFLL, "u2_conv_fwd_mt: source tensor too large for 32-bit element offsets");
-    if (n_dst == 0) return 0;
-    const int KC = pick_kc(Cs), NT = pick_nt(Cd);
-    U2_CHECK_ARG(KC && NT && K <= 32, "u2_conv_fwd_mt: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
-    U2_CHECK_ARG(ld % TILE_M == 0, "u2_conv_fwd_mt: table leading dimension must be a multiple of 128");
-    U2_CHECK_ARG(scratch && scratch_bytes >= (size_t)K * Cs * Cd * sizeof(float), "u2_conv_fwd_mt: scratch too small");
-    U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)scratch) & 15) == 0,
-                 "u2_conv_fwd_mt: pointers must be 16-byte aligned");
-    const int64_t total4 = (int64_t)K * Cs * Cd / 4;
-    if (w_transposed)
-        pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-    else
-        pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-    U2_LAUNCH_OK();
-
-    const int64_t n_tiles = ld / TILE_M;
-    const int n_nt = Cd / NT;
-    // tiles per CTA: as many accumulators as TMEM holds (<= 4), but keep >= ~2 CTAs per SM of work
-    static const int t_max = getenv("U2_CONV_TMAX") ? atoi(getenv("U2_CONV_TMAX")) : 4;
-    int T = 512 / NT >= 4 ? 4 : (512 / NT >= 2 ? 2 : 1);
-    while (T > t_max) T >>= 1;
-    while (T > 1 && (n_tiles / T) * n_nt < 2 * U2_NUM_SMS) T >>= 1;
-    MtParams p;
-    p.X = X; p.Wt = (const float *)scratch; p.table = tableP; p.perm = perm; p.tile_mask = tile_mask; p.Y = Y;
-    p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
-    int cols = 32;
-    while (cols < T * NT) cols <<= 1;
-    p.tmem_cols = cols;
-    const int chunks = KC / 4;
-    const size_t a_bytes = (size_t)chunks * A_LBO, b_bytes = (size_t)chunks * NT * 16;
-    const size_t fixed = (2 * MAX_SA + 2 * MAX_SB + 1) * sizeof(uint64_t) + 16;
-    // two CTAs per SM when TMEM (<= 256 columns each) and shared memory allow, else one big one
-    size_t budget = 113 * 1024;
-    int sb = 2;
-    int sa = cols <= 256 ? (int)((budget - fixed - sb * b_bytes) / a_bytes) : 0;
-    if (cols > 256 || sa < 3 || budget < fixed + sb * b_bytes) {
-        budget = 226 * 1024;
-        sb = 3;
-        sa = (int)((budget - fixed - sb * b_bytes) / a_bytes);
-    }
-    if (sa > MAX_SA) sa = MAX_SA;
-    U2_CHECK_ARG(sa >= 2, "u2_conv_fwd_mt: tile does not fit shared memory");
-    p.sa = sa; p.sb = sb;
-    const size_t smem = sa * a_bytes + sb * b_bytes + fixed;
-    dim3 grid((unsigned)u2_ceil_div(n_tiles, T), (unsigned)n_nt);
-    if (KC == 32) {
-        if (T == 4) return launch_mt<32, 4>(p, grid, smem, st);
-        if (T == 2) return launch_mt<32, 2>(p, grid, smem, st);
-        return launch_mt<32, 1>(p, grid, smem, st);
-    }
-    if (T == 4) return launch_mt<16, 4>(p, grid, smem, st);
-    if (T == 2) return launch_mt<16, 2>(p, grid, smem, st);
-    return launch_mt<16, 1>(p, grid, smem, st);
-}
-
-typedef CUresult (*U2EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static U2EncodeTiledFn get_encode_tiled() {
-    static U2EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (U2EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
-template <int T>
-static int launch_tma(const CUtensorMap &tmap, const TmaParams &p, dim3 grid, size_t smem, cudaStream_t st) {
-    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_fwd_tma_kernel<T><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
-    U2_LAUNCH_OK();
-    return 0;
-}
-
-int u2_conv_fwd_tma_supported(int32_t Cs, int32_t Cd, int32_t K) { return Cs % 32 == 0 && pick_nt(Cd) && K <= 32 && get_encode_tiled(); }
-
-int u2_conv_fwd_tma(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *tableP,
-                    const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y,
-                    void *scratch, size_t scratch_bytes, cudaStream_t st) {
-    if (n_dst == 0) return 0;
-    const int KC = 32, NT = pick_nt(Cd);
-    U2_CHECK_ARG(Cs % 32 == 0 && NT && K <= 32, "u2_conv_fwd_tma: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
-    U2_CHECK_ARG(ld % TILE_M == 0 && ((uintptr_t)tableP & 15) == 0, "u2_conv_fwd_tma: table must be 16-byte aligned, ld %% 128 == 0");
-    U2_CHECK_ARG(scratch && scratch_bytes >= (size_t)K * Cs * Cd * sizeof(float), "u2_conv_fwd_tma: scratch too small");
-    U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)scratch) & 15) == 0,
-                 "u2_conv_fwd_tma: pointers must be 16-byte aligned");
-    U2EncodeTiledFn encode = get_encode_tiled();
-    U2_CHECK_ARG(encode != nullptr, "u2_conv_fwd_tma: cuTensorMapEncodeTiled not available");
-    alignas(64) CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)Cs, (cuuint64_t)(n_src > 0 ? n_src : 1)};
-    const cuuint64_t gstride[1] = {(cuuint64_t)Cs * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)KC, 1u};
-    const cuuint32_t estr[2] = {1u, 1u};
-    CUresult rc = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)X, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    U2_CHECK_ARG(rc == CUDA_SUCCESS, "u2_conv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)rc);
-
-    const int64_t total4 = (int64_t)K * Cs * Cd / 4;
-    if (w_transposed)
-        pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-    else
-        pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-    U2_LAUNCH_OK();
-
-    const int64_t n_tiles = ld / TILE_M;
-    const int n_nt = Cd / NT;
-    int T = 512 / NT >= 4 ? 4 : (512 / NT >= 2 ? 2 : 1);
-    while (T > 1 && (n_tiles / T) * n_nt < 2 * U2_NUM_SMS) T >>= 1;
-    TmaParams p;
-    p.Wt = (const float *)scratch; p.table = tableP; p.perm = perm; p.tile_mask = tile_mask; p.Y = Y;
-    p.ld = ld; p.n_dst = n_dst; p.Cs = Cs; p.Cd = Cd; p.K = K; p.NT = NT;
-    int cols = 32;
-    while (cols < T * NT) cols <<= 1;
-    p.tmem_cols = cols;
-    const size_t a_bytes = (size_t)TILE_M * KC * 4, b_bytes = (size_t)KC * NT * 4;
-    const size_t fixed = (2 * MAX_SA + 2 * MAX_SB + 1) * sizeof(uint64_t) + 16 + 1024;
-    size_t budget = 113 * 1024;
-    int sb = 2;
-    int sa = (cols <= 256 && budget > fixed + sb * b_bytes) ? (int)((budget - fixed - sb * b_bytes) / a_bytes) : 0;
-    if (cols > 256 || sa < 3) {
-        budget = 226 * 1024;
-        sb = 3;
-        sa = (int)((budget - fixed - sb * b_bytes) / a_bytes);
-    }
-    if (sa > MAX_SA) sa = MAX_SA;
-    U2_CHECK_ARG(sa >= 2, "u2_conv_fwd_tma: tile does not fit shared memory");
-    p.sa = sa; p.sb = sb;
-    const size_t smem = sa * a_bytes + sb * b_bytes + fixed;
-    dim3 grid((unsigned)u2_ceil_div(n_tiles, T), (unsigned)n_nt);
-    if (T == 4) return launch_tma<4>(tmap, p, grid, smem, st);
-    if (T == 2) return launch_tma<2>(tmap, p, grid, smem, st);
-    return launch_tma<1>(tmap, p, grid, smem, st);
 }

@@ -31,7 +31,10 @@ class _FusedNormMixin:
             return input
         feats = input.feats if _is_sparse(input) else input
         if feats.dim() != 2:
-            return super().forward(input)
+            # [N, C, L] / [N, C, H, W] input (e.g. BatchNorm2d -> SyncBatchNorm of core/models/fusion_blocks.py:101-103): torch's
+            # kernels, and the ReLU that optimize() folded into this module must still be applied
+            out = super().forward(input)
+            return torch.relu(out) if getattr(self, "_u2_fused_relu", False) else out
         group = ops._bn_group(self)
         out = ops.batch_norm_relu(feats, self, relu=getattr(self, "_u2_fused_relu", False), group=group)
         if not _is_sparse(input):

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
 
 _MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
-_state = {"math": MATH_FP32, "sort_tiles": True, "multi_tile": False, "overlap_rows": 1 << 30}
+_state = {"math": MATH_FP32, "sort_tiles": True, "overlap_rows": 1 << 30}
 
 # instrumentation used by bench.py: number of kernels this library launched, and an optional
 # per-launch CUDA-event timer for the conv kernels (the dominant kernel of the path)
@@ -43,19 +43,23 @@ def set_sort_tiles(flag: bool) -> None:
     _state["sort_tiles"] = bool(flag)
 
 
-def set_multi_tile(flag: bool) -> None:
-    """Multi-tile CTAs for the tensor-core fwd/dgrad conv (weights shared by up to 4 tiles)."""
-    _state["multi_tile"] = bool(flag)
-
-
 def get_math() -> str:
     return {v: k for k, v in _MATH_NAMES.items()}[_state["math"]]
 
 
 def _need_cuda(*tensors):
+    """Operands must live on the CURRENT CUDA device: kernels are launched on its current stream (`_st`)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("u2mkd_b200 ops need CUDA tensors (no CPU fallback); got a tensor on " + str(t.device))
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"u2mkd_b200 ops launch on the current device cuda:{cur}, but an operand lives on {t.device}; "
+                               "wrap the call in torch.cuda.device(tensor.device)")
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -388,7 +392,7 @@ def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math,
         tabP, perm, tmask = kmap.sorted_tables(side)
         _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd_perm(
             x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), tabP.data_ptr(), perm.data_ptr(),
-            tmask.data_ptr() if _state["multi_tile"] else None, ld, n_dst, K, c_dst, y.data_ptr(), math, _ptr(scratch),
+            None, ld, n_dst, K, c_dst, y.data_ptr(), math, _ptr(scratch),
             sbytes, _st())))
         return y
     _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd(
@@ -725,6 +729,7 @@ def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, re
     K, cin, cout = weight.shape
     n_dst = kmap.n_in if transposed else kmap.n_out
     fused = (_state["math"] == MATH_BF16 and _state.get("fuse_conv_bn", True) and bn.training and bn.affine
+             and bn.momentum is not None
              and feats.is_cuda and feats.dtype == torch.float32 and weight.dtype == torch.float32 and n_dst > 1
              and feats.shape[0] > 0 and cout % 32 == 0 and lib().u2_bn_supported(cout)
              and lib().u2_conv_tc_shape_supported(cin, cout, K, MATH_BF16)
@@ -736,7 +741,7 @@ def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, re
             return batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, relu, group)
         out = batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, False, group) + residual
         return torch.relu_(out) if relu else out
-    momentum = 0.1 if bn.momentum is None else bn.momentum
+    momentum = float(bn.momentum)
     _count_batch(bn)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
@@ -747,20 +752,44 @@ def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, re
     return z
 
 
+def _bn_momentum(bn) -> float:
+    """exponential_average_factor of torch's _BatchNorm.forward: `momentum`, or the cumulative average
+    1 / num_batches_tracked when momentum is None (the counter is then bumped eagerly: one host read per call)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        return 1.0 / float(int(bn.num_batches_tracked) + 1)
+    return 0.0
+
+
 def batch_norm_relu(x, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = False, group=None):
-    """BatchNorm(+ReLU) of a feature matrix with the module's parameters / running statistics.
-    Training mode on supported shapes runs the fused kernels; everything else falls back to torch's
-    batch_norm (eval mode, C not a multiple of 4, no affine)."""
+    """BatchNorm(+ReLU) of a feature matrix [n, C] with the module's parameters / running statistics.
+    Training mode on supported shapes runs the fused kernels (with `group`: statistics over all ranks, one fp64
+    all-reduce per pass; a rank with zero rows contributes zero sums).  Shapes the kernels do not cover (C not a
+    multiple of 4, C > 1024, no affine) go to torch: torch's own SyncBatchNorm when `group` is set — never local
+    statistics, and every rank takes the same branch because the decision depends on the module and C only —
+    else F.batch_norm."""
     c = x.shape[1]
     if bn.training and x.shape[0] == 1 and group is None:
         raise ValueError(f"Expected more than 1 value per channel when training, got input size {x.size()}")
-    if (bn.training and x.is_cuda and bn.affine and x.dtype == torch.float32 and lib().u2_bn_supported(c)
-            and x.shape[0] > 0):
-        momentum = 0.1 if bn.momentum is None else bn.momentum
-        _count_batch(bn)
+    if bn.training and x.is_cuda and bn.affine and lib().u2_bn_supported(c) and (x.shape[0] > 0 or group is not None):
+        momentum = _bn_momentum(bn)
+        if bn.momentum is None and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        else:
+            _count_batch(bn)
         rm = bn.running_mean if bn.track_running_stats else None
         rv = bn.running_var if bn.track_running_stats else None
-        return BatchNormFn.apply(x, bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu, group)
-    y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
-                                       0.1 if bn.momentum is None else bn.momentum, bn.eps)
+        y = BatchNormFn.apply(x.float(), bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu, group)
+        return y if x.dtype == torch.float32 else y.to(x.dtype)  # autocast input: fp32 arithmetic, caller's dtype back
+    if group is not None:
+        y = torch.nn.SyncBatchNorm.forward(bn, x)  # torch's synchronized path (handles its own counter / momentum)
+        return torch.relu(y) if relu else y
+    factor = _bn_momentum(bn)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    use_batch_stats = bn.training or (bn.running_mean is None and bn.running_var is None)
+    y = torch.nn.functional.batch_norm(x, bn.running_mean if (not bn.training or bn.track_running_stats) else None,
+                                       bn.running_var if (not bn.training or bn.track_running_stats) else None,
+                                       bn.weight, bn.bias, use_batch_stats, factor, bn.eps)
     return torch.relu(y) if relu else y
