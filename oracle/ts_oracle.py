@@ -406,14 +406,30 @@ def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1)
     return coords
 
 
+# Yardstick for the reduced-precision modes of the product (tests/gradtable.py): with OPERAND_ROUNDING set, every conv
+# GEMM operand (features, weights, output gradients) is rounded to that format before the mm — the same rounding points as
+# the product's bf16 / tf32 tensor-core modes — while everything else keeps the oracle's dtype.  None = the plain oracle.
+OPERAND_ROUNDING = None
+
+
+def _rnd(x: torch.Tensor) -> torch.Tensor:
+    if OPERAND_ROUNDING is None:
+        return x
+    if OPERAND_ROUNDING == "bf16":
+        return x.bfloat16().to(x.dtype)
+    if OPERAND_ROUNDING == "tf32":  # the tensor core truncates fp32 to 10 mantissa bits
+        return (x.float().contiguous().view(torch.int32) & -8192).view(torch.float32).to(x.dtype)
+    raise ValueError(OPERAND_ROUNDING)
+
+
 class _ConvolutionFn(Function):
     """SURVEY A.11/A.12 [TS nn/functional/conv.py, backend/convolution/convolution_cpu.cpp]:
     per kernel offset gather -> mm -> scatter; centre-tap shortcut iff K odd and N_in == N_out."""
 
     @staticmethod
     def forward(ctx, input, weight, nbmaps, nbsizes, sizes, transposed=False):
-        input = input.contiguous()
-        weight = weight.contiguous()
+        input = _rnd(input.contiguous())
+        weight = _rnd(weight.contiguous())
         nbmaps = nbmaps.int().contiguous()
         nbsizes = nbsizes.int().contiguous()
         n_out = sizes[1] if not transposed else sizes[0]
@@ -447,7 +463,7 @@ class _ConvolutionFn(Function):
     @staticmethod
     def backward(ctx, grad_output):
         input, weight, nbmaps, sizes_list, t = ctx.for_backwards
-        grad_output = grad_output.contiguous()
+        grad_output = _rnd(grad_output.contiguous())
         suf = _suf(input)
         K, cin, cout = weight.shape
         grad_input = torch.zeros_like(input)

@@ -37,6 +37,9 @@ def timeit(fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--modes", default="0,1,2,3,4,5")
+    ap.add_argument("--shapes", default="all")
+    ap.add_argument("--stats", action="store_true", help="run the conv with the fused BatchNorm statistics epilogue")
     args = ap.parse_args()
     ops.set_math("bf16")
     coords, _ = scans.make_batch([0, 1], "nusc", 5, 0.05)
@@ -49,12 +52,15 @@ def main():
         km = ops.build_kernel_map(vox, vox, get_kernel_offsets(3, stride, 1, device="cuda"))
         maps[stride] = (vox.shape[0], km, int(km.nbsizes.sum()))
     rows = []
-    for stride, cin, cout in ((1, 64, 64), (1, 128, 128), (1, 192, 192), (1, 256, 192), (8, 256, 256), (8, 512, 512), (8, 768, 512)):
+    shapes = ((1, 64, 64), (1, 128, 128), (1, 192, 192), (1, 256, 192), (8, 256, 256), (8, 512, 512), (8, 768, 512))
+    if args.shapes != "all":
+        shapes = tuple(tuple(int(v) for v in sh.split("x")) for sh in args.shapes.split(","))
+    for stride, cin, cout in shapes:
         n, km, M = maps[stride]
         x = ops.cast_bf16(torch.randn(n, cin, device="cuda"))
         w = torch.randn(27, cin, cout, device="cuda") * 0.05
         r = {"stride": stride, "cin": cin, "cout": cout, "n": n, "pairs": M}
-        for mode in (0, 1, 2, 3, 4, 5):
+        for mode in [int(m) for m in args.modes.split(",")]:
             os.environ["U2_CONV_DIAG"] = str(mode)
             r[f"ms_diag{mode}"] = round(timeit(lambda: ops._conv_gather_gemm("fwd", km, x, w, False, km.nbr, n, cout, 2, side=False), args.reps), 4)
         os.environ["U2_CONV_DIAG"] = "0"

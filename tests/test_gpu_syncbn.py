@@ -67,8 +67,13 @@ def _run(net, coords, feats, dev):
         x = feats.to(dev).requires_grad_(True)
         y = net["vox"](gts.SparseTensor(x, coords.to(dev)))
         z = net["pts"](y.F)
+        from u2mkd_b200 import ops
+        ops.flush_bn_counters()  # fusion.optimize hooks this onto the forward of the module it was given (never called here)
         gy = torch.from_numpy(np.random.default_rng(5).standard_normal((1, 48)).astype(np.float32)).to(dev)
-        (z * gy).sum().backward()
+        gv = torch.from_numpy(np.random.default_rng(6).standard_normal((1, 64)).astype(np.float32)).to(dev)
+        # the second term keeps sum_rows(dL/dy) away from zero (behind a BatchNorm alone it cancels exactly and the
+        # gradient of the last voxel BatchNorm's bias would be rounding noise)
+        ((z * gy).sum() + (y.F * gv).sum() + 0.1 * y.F.square().sum()).backward()
         torch.cuda.synchronize(dev)
     finally:
         u2mkd_b200.set_math("fp32")
@@ -124,6 +129,8 @@ def test_sync_batchnorm_group_path_matches_concatenated_batch(cuda_lib):
         assert _rel(both, ref[k]) < 2e-3, (k, _rel(both, ref[k]))
         assert _rel(got[0][k], ref[k][:n0]) < 2e-3 and _rel(got[1][k], ref[k][n0:]) < 2e-3, k
     for k in ref:
+        if k == "g:pts.0.bias":
+            continue  # zero in exact arithmetic (bias in front of a BatchNorm): rounding noise on both sides
         if k.startswith("g:"):
             # parameter gradients are LOCAL sums on each rank (DistributedDataParallel averages them afterwards)
             assert _rel(got[0][k] + got[1][k], ref[k]) < 3e-3, (k, _rel(got[0][k] + got[1][k], ref[k]))

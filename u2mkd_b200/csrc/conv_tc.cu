@@ -169,36 +169,6 @@ struct FwdParams {
     int diag;  // U2_CONV_DIAG (timing diagnostics, results invalid): 1 = no weight loads, 2 = no gathers, 4 = gathers hit 128 hot rows
 };
 
-// Column sums over the 32 rows a warp holds (lane = row, r[j] = column j): a transposing butterfly, 31 shuffles
-// instead of 32 x 5; on return lane l holds the sum of column l.
-__device__ __forceinline__ float warp_colsum32(float (&r)[32], int lane) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; i++) {
-            const float send = up ? r[i] : r[i + o];
-            const float keep = up ? r[i + o] : r[i];
-            r[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, o);
-        }
-    }
-    return r[0];
-}
-
-// columns [c, c + 32) of this warp's 32 accumulator rows -> tile_stats (sum, then sum of squares)
-__device__ __forceinline__ void stats32(const uint32_t (&a)[16], const uint32_t (&b)[16], int lane, float *ts, int Cd) {
-    float r[32];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { r[i] = __uint_as_float(a[i]); r[16 + i] = __uint_as_float(b[i]); }
-    ts[lane] = warp_colsum32(r, lane);
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        r[i] = __uint_as_float(a[i]) * __uint_as_float(a[i]);
-        r[16 + i] = __uint_as_float(b[i]) * __uint_as_float(b[i]);
-    }
-    ts[Cd + lane] = warp_colsum32(r, lane);
-}
-
 // ROWB = bytes of one gathered row per pipeline stage (128 or 64): 32/16 fp32 or 64/32 bf16 channels.
 template <int ROWB, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParams p) {
@@ -230,7 +200,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     if (tid == 0) {
         *s_mask = 0;
         for (int s = 0; s < p.stages; s++) {
-            mbar_init(s_full + s, TILE_M + 1);
+            mbar_init(s_full + s, (p.diag & 8) ? 4 + 1 : TILE_M + 1);
             mbar_init(s_empty + s, 1);
         }
         mbar_init(s_accum, 1);
@@ -346,75 +316,77 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                     if (!(p.diag & 2))
                         cp_async16_mode(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u, p.cp_mode);
                 }
-                cp_async_mbar_arrive_noinc(s_full + s);
+                if (!(p.diag & 8) || lane == 0) cp_async_mbar_arrive_noinc(s_full + s);  // diag 8: one arrival per warp (racy)
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
         // ============================ epilogue ============================
+        // TMEM -> registers (lane = row) -> shared memory (the idle pipeline stages, XOR-swizzled 16-byte chunks) ->
+        // coalesced global stores: 8 lanes write the 128 contiguous bytes of one row, 4 rows per instruction.  (Storing
+        // straight from the TMEM registers makes every st.global.v4 touch 32 different rows: measured 28 % of the
+        // kernel on the stride-1 layers, U2_CONV_DIAG=16.)
         if (dbg && tid == 0) { dbg[2] = clock64(); dbg[8] = dbg_wait; }
         const int64_t trow = row0 + warp * 32 + lane;
         int64_t row = trow;
         if (p.perm) row = __ldg(p.perm + trow);
-        const bool live = row >= 0 && row < p.n_dst;
-        float *yrow = p.Y + (live ? row : 0) * p.Cd + nt * NT;
+        const int my_dst = (row >= 0 && row < p.n_dst && !(p.diag & 16)) ? (int)row : -1;  // diag 16: no output stores
         if (n_items > 0) {
             mbar_wait(s_accum, 0);
             tc_fence_after();
             if (dbg && tid == 0) dbg[3] = clock64();
-            // 64 accumulator columns per round: four tcgen05.ld in flight, one wait
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
             // rows without a destination (padding of the sorted table) have no neighbours: their accumulators are 0
-            float *ts = p.tile_stats ? p.tile_stats + ((size_t)blockIdx.x * 4 + warp) * 2 * p.Cd + nt * NT : nullptr;
-            int c0 = 0;
-            for (; c0 + 64 <= NT; c0 += 64) {
-                uint32_t v0[16], v1[16], v2[16], v3[16];
-                tmem_ld16(t_row + (uint32_t)c0, v0);
-                tmem_ld16(t_row + (uint32_t)c0 + 16, v1);
-                tmem_ld16(t_row + (uint32_t)c0 + 32, v2);
-                tmem_ld16(t_row + (uint32_t)c0 + 48, v3);
-                tmem_ld_wait();
-                if (live) {
+            float *ts = (p.tile_stats && !(p.diag & 32)) ? p.tile_stats + ((size_t)blockIdx.x * 4 + warp) * 2 * p.Cd + nt * NT : nullptr;
+            uint8_t *stg = smem + warp * 4096;            // this warp's 32 rows x 128 B staging tile (inside stage 0)
+            const uint32_t stg_u32 = smem_u32(stg);
+            const int rsub = lane >> 3, cj = lane & 7;    // store phase: row within a group of 4, 16-byte chunk of the row
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                const int ncol = min(32, NT - c0);        // 32, or 16 for the last chunk when NT % 32 == 16
+                uint32_t v[32];
+                {
+                    uint32_t lo[16], hi[16];
+                    tmem_ld16(t_row + (uint32_t)c0, lo);
+                    if (ncol == 32) tmem_ld16(t_row + (uint32_t)c0 + 16, hi);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-                        *reinterpret_cast<uint4 *>(yrow + c0 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
-                        *reinterpret_cast<uint4 *>(yrow + c0 + 32 + j) = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
-                        *reinterpret_cast<uint4 *>(yrow + c0 + 48 + j) = make_uint4(v3[j], v3[j + 1], v3[j + 2], v3[j + 3]);
+                    for (int j = 0; j < 16; j++) { v[j] = lo[j]; v[16 + j] = ncol == 32 ? hi[j] : 0u; }
+                }
+                __syncwarp();  // the previous chunk's readers are done with the staging tile
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u32 + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                                 "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                                 : "memory");
+                __syncwarp();
+                if (ts && ncol == 32) {
+                    // column `lane` over the warp's 32 rows: one conflict-free 4-byte read per row
+                    float sum = 0.f, sq = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < 32; r++) {
+                        const float x = *reinterpret_cast<const float *>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                        sum += x;
+                        sq = fmaf(x, x, sq);
                     }
+                    ts[c0 + lane] = sum;
+                    ts[p.Cd + c0 + lane] = sq;
                 }
-                if (ts) {
-                    stats32(v0, v1, lane, ts + c0, p.Cd);
-                    stats32(v2, v3, lane, ts + c0 + 32, p.Cd);
-                }
-            }
-            if (c0 + 32 <= NT) {
-                uint32_t v0[16], v1[16];
-                tmem_ld16(t_row + (uint32_t)c0, v0);
-                tmem_ld16(t_row + (uint32_t)c0 + 16, v1);
-                tmem_ld_wait();
-                if (live) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-                        *reinterpret_cast<uint4 *>(yrow + c0 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+                for (int i = 0; i < 8; i++) {
+                    const int r = 4 * i + rsub;
+                    const int dst = __shfl_sync(0xFFFFFFFFu, my_dst, r);  // all lanes take part, whatever ncol is
+                    if (dst >= 0 && cj * 4 < ncol) {
+                        uint4 q;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                                     : "r"(stg_u32 + r * 128 + ((cj ^ (r & 7)) << 4)));
+                        *reinterpret_cast<uint4 *>(p.Y + (int64_t)dst * p.Cd + nt * NT + c0 + cj * 4) = q;
                     }
-                }
-                if (ts) stats32(v0, v1, lane, ts + c0, p.Cd);
-                c0 += 32;
-            }
-            for (; c0 < NT; c0 += 16) {  // NT % 32 == 16: the launcher refuses tile_stats for such shapes
-                uint32_t v[16];
-                tmem_ld16(t_row + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<uint4 *>(yrow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             }
         } else {
-            if (live)
+            if (my_dst >= 0) {
+                float *yrow = p.Y + (int64_t)my_dst * p.Cd + nt * NT;
                 for (int c0 = 0; c0 < NT; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
+            }
             if (p.tile_stats) {
                 float *ts = p.tile_stats + ((size_t)blockIdx.x * 4 + warp) * 2 * p.Cd + nt * NT;
                 for (int c = lane; c < NT; c += 32) { ts[c] = 0.f; ts[p.Cd + c] = 0.f; }
