@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: scripts/gpurun_retry.sh <outfile> <timeout> <command...>   — retries while the pod answers busy (exit 3 / transient)
+out=$1; shift; to=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout $to -- "$@" > $out 2>&1
+  rc=$?
+  if grep -q "status=transient" $out || [ $rc -eq 3 ]; then sleep 90; continue; fi
+  break
+done
+echo "rc=$rc" >> $out

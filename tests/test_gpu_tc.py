@@ -382,3 +382,84 @@ def test_dgrad_wgrad_stream_overlap_does_not_change_gradients(tc):
     finally:
         ops.set_overlap_rows(saved)
         tc.set_math("fp32")
+
+
+@pytest.mark.parametrize("n,cin,cout", [(5000, 64, 128), (3000, 768, 512), (2100, 256, 192), (129, 64, 64)])
+def test_k1_conv_on_identity_map_bf16(tc, oracle, n, cin, cout):
+    """1x1x1 conv (ResidualBlock shortcut, core/models/build_blocks.py:74-78) in bf16 mode: the tcgen05 kernels over an
+    identity kernel map instead of cuBLAS; against the oracle's matmul, north_star's bf16 bar."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin)
+    c = rand_coords(rng, n)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32))
+    conv_o, conv_g = oracle.Conv3d(cin, cout, 1), gts.nn.Conv3d(cin, cout, 1)
+    conv_g.load_state_dict(conv_o.state_dict())
+    conv_g.cuda()
+    fo = f.clone().requires_grad_(True)
+    yo = conv_o(oracle.SparseTensor(fo, c))
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    tc.set_math("bf16")
+    try:
+        before = tc.stats["launches"]
+        fg = f.clone().cuda().requires_grad_(True)
+        yg = conv_g(gts.SparseTensor(fg, c.cuda()))
+        yg.F.backward(g.cuda())
+        assert tc.stats["launches"] > before  # our kernels ran (a cuBLAS matmul would not count)
+    finally:
+        tc.set_math("fp32")
+    assert conv_g.kernel.grad.shape == conv_o.kernel.grad.shape
+    assert rel_err(yg.F, yo.F) < TF32_REL
+    assert rel_err(fg.grad, fo.grad) < TF32_REL
+    assert rel_err(conv_g.kernel.grad, conv_o.kernel.grad) < TF32_REL
+
+
+@pytest.mark.parametrize("n,cin,cout,relu", [(6000, 64, 512, True), (4000, 512, 256, True), (3000, 256, 192, False)])
+def test_linear_bn_relu_fused_matches_torch_modules(tc, n, cin, cout, relu):
+    """Sequential(Linear, BatchNorm1d[, ReLU]) of the point branch (core/models/semantickitti/spvcnn.py:58-76) as one fused
+    node on the tcgen05 kernels, against the same modules in torch fp64 fed the SAME bf16-rounded GEMM operands (so that
+    the ReLU masks agree: a mask that flips because the forward differs by a bf16 rounding changes one of ~cout/2 terms
+    of a dx row by O(1), which is the arithmetic of the mode, not of the kernel — the plain fp64 reference sits at
+    ~1e-1 from ANY bf16 forward in dx).  bf16 bar for outputs and gradients, the bias gradient exactly zero (it is zero
+    in exact arithmetic), running statistics including the bias."""
+    from u2mkd_b200 import fusion
+    torch.manual_seed(n)
+    layers = [torch.nn.Linear(cin, cout), torch.nn.BatchNorm1d(cout)] + ([torch.nn.ReLU(True)] if relu else [])
+    ref = torch.nn.Sequential(*layers).double()
+    with torch.no_grad():
+        ref[1].weight.uniform_(0.5, 1.5)
+        ref[1].bias.uniform_(-0.5, 0.5)
+        ref[0].bias.uniform_(-1.0, 1.0)
+        ref[0].weight.copy_(ref[0].weight.float().bfloat16().double())  # weights exactly representable in bf16
+    layers = [torch.nn.Linear(cin, cout), torch.nn.BatchNorm1d(cout)] + ([torch.nn.ReLU(True)] if relu else [])
+    seq = torch.nn.Sequential(*layers)
+    seq.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in ref.state_dict().items()})
+    seq.cuda()
+    fusion.optimize(seq)
+    assert "forward" in seq.__dict__
+    x = torch.randn(n, cin).bfloat16().float()                          # inputs exactly representable in bf16
+    g = torch.randn(n, cout)
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(g.double())
+    tc.set_math("bf16")
+    try:
+        before = tc.stats["launches"]
+        xg = x.cuda().requires_grad_(True)
+        yg = seq(xg)
+        yg.backward(g.cuda())
+        assert tc.stats["launches"] - before >= 6
+    finally:
+        tc.set_math("fp32")
+    assert rel_err(yg, yr) < 1e-4                                        # same operands, fp32 accumulation
+    assert rel_err(xg.grad, xr.grad) < TF32_REL                          # dy is rounded to bf16 for dgrad / wgrad
+    assert rel_err(seq[0].weight.grad, ref[0].weight.grad) < TF32_REL
+    assert rel_err(seq[1].weight.grad, ref[1].weight.grad) < 1e-3 and rel_err(seq[1].bias.grad, ref[1].bias.grad) < 1e-3
+    assert seq[0].bias.grad is not None and float(seq[0].bias.grad.abs().max()) == 0.0
+    assert rel_err(seq[1].running_mean, ref[1].running_mean) < 1e-4 and rel_err(seq[1].running_var, ref[1].running_var) < 1e-3
+    assert int(seq[1].num_batches_tracked) == 1
+    # eval mode takes the unchanged module chain
+    seq.eval()
+    ref.eval()
+    with torch.no_grad():
+        assert rel_err(seq(x.cuda()), ref(x.double())) < 1e-4

@@ -69,6 +69,9 @@ __device__ __forceinline__ void cp_async16_mode(uint32_t dst, const void *src, u
     else if (mode == 3) asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
     else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -188,6 +191,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     uint64_t *s_accum = s_empty + MAX_STAGES;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_accum + 1);
     uint32_t *s_mask = s_tmem + 1;
+    uint32_t *s_pm = s_mask + 1;                                   // [K][4]  presence mask of every 32-row quarter
+    uint32_t *s_dirty = s_pm + p.K * 4;                            // [MAX_STAGES][4] rows of a stage that hold data
+    int *s_cnt = reinterpret_cast<int *>(s_dirty + MAX_STAGES * 4);  // [K]     rows present at this offset
+    uint8_t *s_list = reinterpret_cast<uint8_t *>(s_cnt + p.K);    // [K][128] their tile rows, ascending
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
@@ -197,10 +204,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
     const int n_cc = p.Cs * ES / ROWB;
     const int n_nt = p.Cd / NT;
 
+    if (tid < MAX_STAGES * 4) s_dirty[tid] = 0xFFFFFFFFu;  // a stage starts with stale shared memory in every row
     if (tid == 0) {
         *s_mask = 0;
         for (int s = 0; s < p.stages; s++) {
-            mbar_init(s_full + s, (p.diag & 8) ? 4 + 1 : TILE_M + 1);
+            mbar_init(s_full + s, TILE_M + 1);
             mbar_init(s_empty + s, 1);
         }
         mbar_init(s_accum, 1);
@@ -227,13 +235,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         for (int j = 0; j < MAXJ; j++) {
             const int k = warp + j * (NUM_THREADS / 32);
             if (k < p.K) {
-                bool any = false;
+                // compact list of the rows that have a neighbour at this offset: the producers fetch those and only those
+                int cnt = 0;
 #pragma unroll
                 for (int i = 0; i < TILE_M / 32; i++) {
                     s_tab[k * TILE_M + lane + 32 * i] = v[j][i];
-                    any |= v[j][i] >= 0;
+                    const uint32_t b = __ballot_sync(0xffffffffu, v[j][i] >= 0);
+                    if (v[j][i] >= 0) s_list[k * TILE_M + cnt + __popc(b & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * i);
+                    if (lane == 0) s_pm[k * 4 + i] = b;
+                    cnt += __popc(b);
                 }
-                if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(s_mask, 1u << k);
+                if (lane == 0) {
+                    s_cnt[k] = cnt;
+                    if (cnt) atomicOr(s_mask, 1u << k);
+                }
             }
         }
     }
@@ -247,58 +262,35 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
 
     if (warp < 4) {
         // ============================ A producers ============================
-        const int chunk = tid % CHUNKS;
-        const uint32_t dst0 = (uint32_t)(chunk * A_LBO + (tid / CHUNKS) * 16);
+        // Per (offset, channel slice) item only the PRESENT rows are fetched: present row j of the offset's compact list goes
+        // to lane group j % ROWS_PER_IT (CHUNKS lanes, one 16-byte piece each), so an item costs ceil(m / (32 / CHUNKS))
+        // warp-level LDGSTS instead of TILE_M / (32 / CHUNKS).  That matters because the gather is bound by the LDGSTS
+        // instruction rate of the SM (~20-25 cycles per warp instruction whatever it fetches: a zero-fill copy costs as
+        // much as a real one; scripts/microbench/gather_bench.cu, profiles/r2_gather_microbench.md) and ~47 % of the
+        // row slots of the mask-sorted tiles are empty.  Rows that are absent now but still hold data of the stage's
+        // previous item are cleared with plain shared-memory stores (warp w owns rows 32 w .. 32 w + 31).
+        const int chunk = tid % CHUNKS, grp = tid / CHUNKS;
         int s = 0;
         uint32_t ph = 0;
         long long dbg_wait = 0;
-        if (p.cp_mode == 9) {
-            // Register-staged variant: LDG.128 -> STS.128 instead of LDGSTS (the LSU spends ~16 cycles per warp-level
-            // LDGSTS.128; plain loads + stores are cheaper per byte).  The loads of item i+1 are in flight while
-            // item i is stored, so two items of gathers per producer warp hide the L2 latency.
-            uint4 cur[CHUNKS], nxt[CHUNKS];
-            uint32_t m = kmask;
-            int cc = 0;
-            auto issue = [&](uint4 (&v)[CHUNKS], uint32_t mm, int c) {
-                const int k = __ffs(mm) - 1;
-                const int *tab_k = s_tab + k * TILE_M + tid / CHUNKS;
-                const uint8_t *xc = p.X + (size_t)c * ROWB + chunk * 16;
-#pragma unroll
-                for (int i = 0; i < CHUNKS; i++) {
-                    const int src = tab_k[i * ROWS_PER_IT];
-                    v[i] = src >= 0 ? __ldg(reinterpret_cast<const uint4 *>(xc + (size_t)src * (size_t)(p.Cs * ES)))
-                                    : make_uint4(0u, 0u, 0u, 0u);
-                }
-            };
-            if (n_items > 0) issue(nxt, m, 0);
-            for (int it = 0; it < n_items; it++) {
-#pragma unroll
-                for (int i = 0; i < CHUNKS; i++) cur[i] = nxt[i];
-                if (++cc == n_cc) { cc = 0; m &= m - 1; }
-                if (it + 1 < n_items) issue(nxt, m, cc);
-                mbar_wait(s_empty + s, ph ^ 1u);
-                const uint32_t a_dst = smem_u32(s_stage + (size_t)s * stage_bytes) + dst0;
-#pragma unroll
-                for (int i = 0; i < CHUNKS; i++)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_dst + i * (ROWS_PER_IT * 16)), "r"(cur[i].x),
-                                 "r"(cur[i].y), "r"(cur[i].z), "r"(cur[i].w)
-                                 : "memory");
-                proxy_fence_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                mbar_arrive(s_full + s);
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
-            }
-        } else
         for (uint32_t m = kmask; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
-            const int *tab_k = s_tab + k * TILE_M + tid / CHUNKS;
-            // per-offset setup: element offset of this thread's 16-byte piece in each of its rows
-            uint32_t off[CHUNKS];
+            const int cnt = s_cnt[k];
+            const uint32_t pm = s_pm[k * 4 + warp];
+            // per-offset setup: global byte offset and shared-memory offset of this thread's piece in each of its rounds
+            uint32_t off[CHUNKS], dsto[CHUNKS];
 #pragma unroll
             for (int i = 0; i < CHUNKS; i++) {
-                const int src = tab_k[i * ROWS_PER_IT];
-                off[i] = src >= 0 ? (uint32_t)src * (uint32_t)(p.Cs * ES) + (uint32_t)(chunk * 16) : 0xFFFFFFFFu;  // bytes
-                if (p.diag & 4)
-                    off[i] = (uint32_t)(tid / CHUNKS + i * ROWS_PER_IT) * (uint32_t)(p.Cs * ES) + (uint32_t)(chunk * 16);
+                const int j = grp + i * ROWS_PER_IT;
+                if (j < cnt) {
+                    const int slot = s_list[k * TILE_M + j];
+                    const int src = (p.diag & 4) ? slot : s_tab[k * TILE_M + slot];
+                    off[i] = (uint32_t)src * (uint32_t)(p.Cs * ES) + (uint32_t)(chunk * 16);
+                    dsto[i] = (uint32_t)(chunk * A_LBO + slot * 16);
+                } else {
+                    off[i] = 0xFFFFFFFFu;
+                    dsto[i] = 0u;
+                }
             }
             const uint8_t *xc = p.X;
             for (int cc = 0; cc < n_cc; cc++, xc += ROWB) {
@@ -309,22 +301,35 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                 } else {
                     mbar_wait(s_empty + s, ph ^ 1u);
                 }
-                const uint32_t a_dst = smem_u32(s_stage + (size_t)s * stage_bytes) + dst0;
+                const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
+                const uint32_t stale = s_dirty[s * 4 + warp] & ~pm;
+                if (stale) {  // warp-uniform
+                    if ((stale >> lane) & 1u) {
+#pragma unroll
+                        for (int c = 0; c < CHUNKS; c++)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + c * A_LBO + (warp * 32 + lane) * 16), "r"(0)
+                                         : "memory");
+                    }
+                    proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                }
+                __syncwarp();
+                if (lane == 0) s_dirty[s * 4 + warp] = pm;
 #pragma unroll
                 for (int i = 0; i < CHUNKS; i++) {
-                    const bool ok = off[i] != 0xFFFFFFFFu;
-                    if (!(p.diag & 2))
-                        cp_async16_mode(a_dst + i * (ROWS_PER_IT * 16), xc + (ok ? off[i] : 0u), ok ? 16u : 0u, p.cp_mode);
+                    if (i * ROWS_PER_IT + (warp * 32) / CHUNKS < cnt) {  // warp-uniform: this round has rows for this warp
+                        if (off[i] != 0xFFFFFFFFu && !(p.diag & 2)) cp_async16_ca(a_base + dsto[i], xc + off[i]);
+                    }
                 }
-                if (!(p.diag & 8) || lane == 0) cp_async_mbar_arrive_noinc(s_full + s);  // diag 8: one arrival per warp (racy)
+                cp_async_mbar_arrive_noinc(s_full + s);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
         // ============================ epilogue ============================
         // TMEM -> registers (lane = row) -> shared memory (the idle pipeline stages, XOR-swizzled 16-byte chunks) ->
-        // coalesced global stores: 8 lanes write the 128 contiguous bytes of one row, 4 rows per instruction.  (Storing
-        // straight from the TMEM registers makes every st.global.v4 touch 32 different rows: measured 28 % of the
-        // kernel on the stride-1 layers, U2_CONV_DIAG=16.)
+        // coalesced global stores: 8 lanes write the 128 contiguous bytes of one row, 4 rows per instruction; the fused
+        // BatchNorm column sums are read from the same staging tile.  (The fp32 output write is ~25 % of the kernel on the
+        // stride-1 layers, U2_CONV_DIAG=16, and it is the HBM traffic itself: storing straight from the TMEM registers,
+        // 32 rows per instruction, takes the same time.)
         if (dbg && tid == 0) { dbg[2] = clock64(); dbg[8] = dbg_wait; }
         const int64_t trow = row0 + warp * 32 + lane;
         int64_t row = trow;
@@ -908,7 +913,9 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     p.tmem_cols = cols;
     const int chunks = ROWB / 16;
     const size_t stage_bytes = (size_t)chunks * A_LBO + (size_t)chunks * NT * 16;
-    const size_t fixed = (size_t)K * TILE_M * sizeof(int) + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
+    // neighbour table + per-offset compact row lists / presence masks / counts + per-stage dirty masks + barriers
+    const size_t fixed = (size_t)K * TILE_M * sizeof(int) + (size_t)K * (TILE_M + 16 + 4) + MAX_STAGES * 16 +
+                         (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
     // prefer two CTAs per SM (one gathers while the other drains its accumulator) if that
     // still leaves >= 3 stages each; otherwise one CTA with as many stages as fit
     const size_t budget = 227 * 1024;

@@ -9,7 +9,9 @@ model (core/models/build_blocks.py:21-84) and only changes how two kinds of modu
     epilogue (ops.ConvBNReLUFn): statistics from the conv kernel, bf16 operands for the next conv and for
     the backward convs written by the BatchNorm kernels instead of separate cast passes;
   * the tail of a ResidualBlock, relu(net(x) + downsample(x)) (core/models/build_blocks.py:53-84), runs inside the
-    BatchNorm epilogue of net's last conv: no separate add / ReLU passes over the block output.
+    BatchNorm epilogue of net's last conv: no separate add / ReLU passes over the block output;
+  * Sequential(Linear, BatchNorm1d[, ReLU]) (the point MLPs, core/models/semantickitti/spvcnn.py:58-76) and the 1x1x1
+    shortcut convs run on the same tcgen05 kernels over an identity kernel map, with the same fused BatchNorm epilogue.
 """
 from __future__ import annotations
 
@@ -77,6 +79,30 @@ def _residual_forward(block):
     return forward
 
 
+def _linear_bn_forward(seq):
+    """forward of Sequential(Linear, BatchNorm1d[, ReLU]) (point MLPs, core/models/semantickitti/spvcnn.py:58-76): one fused
+    node on the tcgen05 kernels when ops.linear_bn_relu covers it, the unchanged module chain otherwise."""
+    lin, bn = list(seq.children())[:2]
+
+    def forward(x):
+        out = None
+        if torch.is_tensor(x) and not getattr(bn, "_u2_absorbed", False):
+            out = ops.linear_bn_relu(x, lin, bn, bool(getattr(bn, "_u2_fused_relu", False)))
+        return out if out is not None else nn.Sequential.forward(seq, x)
+
+    return forward
+
+
+def _is_linear_bn(m) -> bool:
+    if not isinstance(m, nn.Sequential) or "forward" in m.__dict__:
+        return False
+    kids = list(m.children())
+    if len(kids) not in (2, 3) or not isinstance(kids[0], nn.Linear) or not isinstance(kids[1], _FusedNormMixin):
+        return False
+    # a third child must be the ReLU that fuse_relu folded into the BatchNorm (its forward is the identity now)
+    return len(kids) == 2 or (isinstance(kids[2], nn.ReLU) and getattr(kids[2], "_u2_skip", False))
+
+
 def _is_residual_block(m) -> bool:
     if type(m).__name__ != "ResidualBlock" or not all(hasattr(m, a) for a in ("net", "downsample", "relu")):
         return False
@@ -121,4 +147,7 @@ def optimize(model: nn.Module, fuse_relu: bool = True, fuse_conv_bn: bool = True
             for m in model.modules():
                 if _is_residual_block(m):
                     m.forward = _residual_forward(m)  # instance attribute: the class and its state_dict stay as they are
+        for m in model.modules():
+            if _is_linear_bn(m):
+                m.forward = _linear_bn_forward(m)
     return model

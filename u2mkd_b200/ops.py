@@ -367,6 +367,75 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets:
     return KernelMap(nbr, nbrT, nbsizes, n_in, n_out, offsets_host, same)
 
 
+_identity_maps = {}
+
+
+def identity_kernel_map(n: int, device) -> KernelMap:
+    """Kernel map of a 1x1x1 conv / a Linear layer over n rows: one offset, row i <-> row i.  With it the dense layers
+    (ResidualBlock shortcut convs core/models/build_blocks.py:74-78, point MLPs core/models/semantickitti/spvcnn.py:58-76)
+    run on the same tcgen05 kernels — and the same fused BatchNorm epilogue — as the k=3 convs instead of cuBLAS.
+    Depends on n only: a small cache serves every layer of a step."""
+    key = (int(n), torch.device(device).index)
+    km = _identity_maps.get(key)
+    if km is None:
+        if len(_identity_maps) >= 32:
+            _identity_maps.pop(next(iter(_identity_maps)))
+        ld = _pad(n)
+        nbr = torch.arange(ld, dtype=torch.int, device=device)
+        nbr[n:] = -1
+        nbr = nbr.view(1, ld)
+        nbsizes = torch.full((1,), n, dtype=torch.int, device=device)
+        km = KernelMap(nbr, nbr, nbsizes, n, n, [[0, 0, 0]], True)
+        km._sorted = {False: (nbr, nbr[0], None), True: (nbr, nbr[0], None)}  # every row has the same mask: nothing to sort
+        km._flat = nbr[0]                                                      # flat pair list k * ld + row = row
+        _count(2)
+        _identity_maps[key] = km
+    return km
+
+
+def dense_tc_supported(cin: int, cout: int) -> bool:
+    """bf16 tcgen05 kernels cover a dense [n, cin] x [cin, cout] layer (fwd, dgrad, wgrad) in the current math mode."""
+    l = lib()
+    return bool(_state["math"] == MATH_BF16 and _state.get("dense_tc", True)
+                and l.u2_conv_tc_shape_supported(cin, cout, 1, MATH_BF16) and l.u2_conv_tc_shape_supported(cout, cin, 1, MATH_BF16)
+                and l.u2_conv_wgrad_pairs_supported(cin, cout, 1, MATH_BF16))
+
+
+class _ZeroGradFor(Function):
+    """y = x, and a zero gradient for `param`: the bias of a Linear in front of a training-mode BatchNorm cancels out of
+    the output, its exact gradient is 0 (the BatchNorm backward sums to zero over the rows)."""
+
+    @staticmethod
+    def forward(ctx, x, param):
+        ctx.shape, ctx.dtype, ctx.device = param.shape, param.dtype, param.device
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, torch.zeros(ctx.shape, dtype=ctx.dtype, device=ctx.device)
+
+
+def linear_bn_relu(x, linear: torch.nn.Linear, bn, relu: bool):
+    """Sequential(Linear, BatchNorm1d[, ReLU]) of the point branch (spvcnn.py:58-76) as one fused node on the tcgen05
+    kernels; None if the layer / mode is not covered (caller falls back to the torch modules)."""
+    cout, cin = linear.weight.shape
+    if not (bn.training and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] > 1
+            and bn.momentum is not None and dense_tc_supported(cin, cout) and cout % 32 == 0):
+        return None
+    km = identity_kernel_map(x.shape[0], x.device)
+    w = linear.weight.t().contiguous().unsqueeze(0)  # [1, cin, cout], the conv kernels' layout (autograd transposes back)
+    out = sparse_conv_bn_relu(x, w, km, False, bn, relu)
+    if linear.bias is not None:
+        if bn.track_running_stats and bn.running_mean is not None:
+            with torch.no_grad():  # the statistics were taken without the bias: mean(xW + b) = mean(xW) + b
+                bn.running_mean.add_(linear.bias.detach(), alpha=float(bn.momentum))
+        stash = getattr(out, "_u2_bf16", None)
+        out = _ZeroGradFor.apply(out, linear.bias)
+        if stash is not None:
+            out._u2_bf16 = (stash[0], out._version)
+    return out
+
+
 # -------------------------------------------------------------------------------- convolution
 def _timed(kind, kmap, n_dst, K, c_src, c_dst, launch):
     """Run `launch()`; if bench.py installed a conv timer, bracket it with CUDA events on the

@@ -46,8 +46,18 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
     kernel_size, stride, dilation = (make_ntuple(v, ndim=3) for v in (kernel_size, stride, dilation))
     unit = (1, 1, 1)
     if kernel_size == unit and stride == unit and dilation == unit:
-        feats = feats.matmul(weight)
         out_stride = input.stride
+        if feats.is_cuda and feats.dim() == 2 and weight.dim() == 2 and feats.shape[0] > 1 and ops.dense_tc_supported(*weight.shape):
+            # bf16 mode: the dense layer runs on the tcgen05 conv kernels over an identity kernel map (no cuBLAS), with the
+            # BatchNorm epilogue fused like every other conv
+            kmap = ops.identity_kernel_map(feats.shape[0], feats.device)
+            if epilogue is not None and bias is None:
+                feats = ops.sparse_conv_bn_relu(feats, weight.unsqueeze(0), kmap, False, *epilogue, residual=residual)
+                epilogue = None
+            else:
+                feats = ops.sparse_conv(feats, weight.unsqueeze(0), kmap, transposed=False)
+        else:
+            feats = feats.matmul(weight)
     elif not transposed:
         out_stride = tuple(input.stride[a] * stride[a] for a in range(3))
         key = (input.stride, kernel_size, stride, dilation)
