@@ -165,11 +165,19 @@ int u2_kmap_sort_rows(const int32_t *table, int64_t ld, int64_t n_rows, int32_t 
 /* 1 if (Cs, Cd, K) runs on the tcgen05 kernels in this math mode (else the FFMA kernel is used) */
 int u2_conv_tc_shape_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 /* u2_conv_fwd over a permuted table: tile row j reads tableP[k][j] and writes Y[perm[j], :].
- * tile_mask != NULL selects the multi-tile kernel (weights fetched once per up-to-4 tiles). */
+ * Yadd fp32 [n_dst, Cd] (may be NULL) is added to the result in the epilogue: when the conv is an input-gradient conv
+ * whose input had a second consumer (the shortcut of core/models/build_blocks.py:79-84), the other consumer's gradient
+ * rides along instead of a separate accumulation pass.
+ * W == NULL in u2_conv_fwd / _perm / _stats: `scratch` already holds the weights re-tiled by u2_conv_pretile.          */
 int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
-                     const int32_t *tableP, const int32_t *perm, const uint32_t *tile_mask, int64_t ld, int64_t n_dst,
+                     const int32_t *tableP, const int32_t *perm, const float *Yadd, int64_t ld, int64_t n_dst,
                      int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch, size_t scratch_bytes,
                      u2_stream_t stream);
+/* Re-tile the fp32 parameter W [K, Cin, Cout] into the blobs the tcgen05 kernels stream (replaces the per-launch
+ * re-tiling of [TS backend/convolution/convolution_cuda.cu], which reads `kernel` as is): blob_fwd for W[k]
+ * (u2_conv_scratch_bytes(., K, Cin, Cout, math) bytes), blob_dgrad for W[k]^T (.., Cout, Cin, ..); either may be NULL. */
+int u2_conv_pretile(const float *W, int32_t K, int32_t Cin, int32_t Cout, int32_t math, void *blob_fwd, void *blob_dgrad,
+                    u2_stream_t stream);
 
 /* ---- BatchNorm (+ fused ReLU) over feature matrices fp32 [n, C], training mode: what the reference runs as
  * torch BatchNorm1d / SyncBatchNorm + ReLU on SparseTensor.F after every conv

@@ -20,6 +20,8 @@
 //         12 COMPACTED LDGSTS.ca: only the present rows of an item are fetched, 4 per warp instruction whatever their slots
 //            (ceil(m / 4) instructions instead of 32), absent slots zeroed by STS.128 (upper bound: every absent row, every item)
 //         13 = 12 without the zeroing stores
+//         14 LDGSTS.ca with lane -> (row = lane % 8, chunk = lane / 8 + 4 h): one instruction writes FULL 128-byte
+//            shared-memory lines (8 rows x 16 B of one chunk plane) and reads 64 B of 8 rows (W = 4 only)
 //          9 cp.async.bulk of the WHOLE row (pitch bytes) per present row, one thread per row (item = 128 whole rows)
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(544) gather_kernel(const __grid_constant__ CUt
             if (p.method == 8) cnt = n_prod + 16;
             if (p.method == 9) cnt = 128;
             if (p.method == 11) cnt = p.W;
-            if (p.method == 12 || p.method == 13) cnt = n_prod;
+            if (p.method == 12 || p.method == 13 || p.method == 14) cnt = n_prod;
             mbar_init(full + s, cnt);
             mbar_init(empty + s, 1);
         }
@@ -173,6 +175,26 @@ __global__ void __launch_bounds__(544) gather_kernel(const __grid_constant__ CUt
                                  "r"(v[k].y), "r"(v[k].z), "r"(v[k].w) : "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + s);
+            } else if (p.method == 14) {
+                // warp w owns rows 32 w .. 32 w + 31 (W == 4); instruction (g, h): rows 8 g + lane % 8, chunk 4 h + lane / 8
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int r = warp * 32 + g * 8 + (lane & 7);
+                    const int src = __shfl_sync(0xFFFFFFFFu, cur[g], (lane & 7) * 1);  // placeholder, replaced below
+                    (void)src;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int r = warp * 32 + g * 8 + (lane & 7);
+                    const int srcr = __ldg(rows + r);
+                    const bool ok = srcr >= 0;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int chunk = 4 * h + (lane >> 3);
+                        cp_async16(base + chunk * (2048 + 16) + r * 16, xs + (ok ? (size_t)srcr * p.pitch + chunk * 16 : 0), ok ? 16u : 0u, 0);
+                    }
+                }
+                cp_async_arrive_noinc(full + s);
             } else if (p.method == 12 || p.method == 13) {
                 // compact the present rows of the item (ballot over the 128 indices, 32 per warp-sized group), then fetch
                 // present row j with the 8-lane group j % (n_prod / 8)
@@ -330,7 +352,7 @@ int main(int argc, char **argv) {
     }
     unsigned long long *sink;
     CK(cudaMalloc(&sink, 8));
-    for (int pitch : {128, 384}) {
+    for (int pitch : {128}) {
         const int slices = pitch / 128;
         uint8_t *X;
         CK(cudaMalloc(&X, (size_t)n * pitch));
@@ -365,13 +387,14 @@ int main(int argc, char **argv) {
                 CK(cudaMemcpy(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
                 long long real_rows = 0;
                 for (int v : idx) real_rows += v >= 0;
-                for (int method = 0; method <= 13; method++) {
+                for (int method = 0; method <= 14; method++) {
+                    if (method == 12 || method == 13 || method == 5) continue;
                     if ((method >= 1 && method <= 4) || method == 6 || method == 7 || method == 9 || method == 11 || method == 10 || method == 8) continue;  // measured: slower than 0 / 5 (see profiles/r2_gather_microbench.md)
                     if ((method == 5 || method == 8) && !encode) continue;
                     if (method == 9 && pitch == 128) continue;
                     for (int W : {4, 8}) {
                         if (method == 5 && W < 4) continue;
-                        if ((method == 4 || method == 9) && W != 4) continue;
+                        if ((method == 4 || method == 9 || method == 14) && W != 4) continue;
                         for (int ctas : {1, 2, 3, 4}) {
                             for (int S : {2}) {
                                 if (ctas * (W + 1) > 64 || (size_t)ctas * (S * STAGE + 3072) > 226 * 1024) continue;

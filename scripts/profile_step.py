@@ -48,3 +48,29 @@ tot = sum(e.self_device_time_total for e in ev)
 print(f"total kernel time {tot/2e3:.2f} ms/step over {sum(e.count for e in ev)//2} launches")
 for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:90]:
     print(f"{e.self_device_time_total/2e3:9.3f} ms/step  x{e.count//2:4d}  {e.key[:110]}")
+
+# GPU busy time (union of kernel intervals) vs wall: how long does the GPU sit idle inside a step?
+try:
+    iv = sorted((e.time_range.start, e.time_range.end) for e in prof.events() if e.device_type == DeviceType.CUDA)
+    busy, cur_s, cur_e = 0.0, None, None
+    for a, b in iv:
+        if cur_e is None or a > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = a, b
+        else:
+            cur_e = max(cur_e, b)
+    if cur_e is not None:
+        busy += cur_e - cur_s
+    span = iv[-1][1] - iv[0][0]
+    gaps = []
+    cur_e = None
+    for a, b in iv:
+        if cur_e is not None and a > cur_e:
+            gaps.append(a - cur_e)
+        cur_e = b if cur_e is None else max(cur_e, b)
+    big = sorted(gaps, reverse=True)[:12]
+    print(f"GPU busy {busy/2e3:.2f} ms/step of a {span/2e3:.2f} ms/step span: idle {(span-busy)/2e3:.2f} ms/step in {len(gaps)//2} gaps/step; "
+          f"largest gaps (us): {[round(g, 1) for g in big]}")
+except Exception as e:
+    print("busy/idle analysis failed:", repr(e))

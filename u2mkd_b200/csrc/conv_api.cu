@@ -13,7 +13,9 @@ size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd
 int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
-                   void *scratch, size_t scratch_bytes, float *tile_stats, cudaStream_t st);
+                   void *scratch, size_t scratch_bytes, float *tile_stats, const float *Yadd, cudaStream_t st);
+int u2_conv_pretile_tc(const float *W, int32_t w_transposed, int32_t K, int32_t Cs, int32_t Cd, int32_t math, void *blob,
+                       cudaStream_t st);
 int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
 int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
                      int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
@@ -38,7 +40,8 @@ extern "C" size_t u2_conv_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, in
 
 static int check_common(const void *X, const void *W, const void *table, const void *Y, int32_t Cs, int32_t Cd, int32_t K,
                         int64_t ld, int64_t n_dst, const char *who) {
-    U2_CHECK_ARG(X && W && table && Y, "%s: null pointer", who);
+    (void)W;  // NULL = the scratch buffer already holds the pre-tiled weights (u2_conv_pretile)
+    U2_CHECK_ARG(X && table && Y, "%s: null pointer", who);
     U2_CHECK_ARG(Cs > 0 && Cd > 0 && K > 0, "%s: bad shape Cs=%d Cd=%d K=%d", who, Cs, Cd, K);
     U2_CHECK_ARG(ld >= n_dst, "%s: ld < n_dst", who);
     return 0;
@@ -52,7 +55,8 @@ extern "C" int u2_conv_fwd(const float *X, int64_t n_src, int32_t Cs, const floa
     if (math == U2_MATH_FP32) return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
 #ifdef U2_WITH_TC
     if ((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math))
-        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, nullptr, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, nullptr, st);
+        return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, nullptr, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes, nullptr,
+                              nullptr, st);
     U2_CHECK_ARG(math != U2_MATH_BF16, "u2_conv_fwd: shape Cs=%d Cd=%d K=%d has no bf16 kernel (caller must use TF32/FP32)", Cs, Cd, K);
     if (math == U2_MATH_TF32)  // shapes the MMA tiles cannot hold (e.g. the Cs = 4 stem conv)
         return u2_conv_fwd_simt(X, n_src, Cs, W, w_transposed, table, ld, n_dst, K, Cd, Y, st);
@@ -102,7 +106,7 @@ extern "C" int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb
 }
 
 extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed,
-                                const int32_t *tableP, const int32_t *perm, const uint32_t *tile_mask, int64_t ld,
+                                const int32_t *tableP, const int32_t *perm, const float *Yadd, int64_t ld,
                                 int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math, void *scratch,
                                 size_t scratch_bytes, u2_stream_t stream) {
 #ifdef U2_WITH_TC
@@ -110,9 +114,8 @@ extern "C" int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const
     U2_CHECK_ARG(perm != nullptr, "u2_conv_fwd_perm: null perm");
     U2_CHECK_ARG((math == U2_MATH_TF32 || math == U2_MATH_BF16) && u2_conv_tc_supported(Cs, Cd, K, math),
                  "u2_conv_fwd_perm: unsupported shape/math");
-    (void)tile_mask;
     return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, tableP, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
-                          nullptr, (cudaStream_t)stream);
+                          nullptr, Yadd, (cudaStream_t)stream);
 #else
     u2_set_error("u2_conv_fwd_perm: built without the tcgen05 path");
     return 1;
@@ -134,9 +137,26 @@ extern "C" int u2_conv_fwd_stats(const float *X, int64_t n_src, int32_t Cs, cons
     U2_CHECK_ARG(tile_stats && tile_stats_bytes >= u2_conv_tile_stats_parts(perm ? ld : n_dst) * 2 * Cd * sizeof(float),
                  "u2_conv_fwd_stats: tile_stats too small");
     return u2_conv_fwd_tc(X, n_src, Cs, W, w_transposed, table, perm, ld, n_dst, K, Cd, Y, math, scratch, scratch_bytes,
-                          tile_stats, (cudaStream_t)stream);
+                          tile_stats, nullptr, (cudaStream_t)stream);
 #else
     u2_set_error("u2_conv_fwd_stats: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+// Both weight blobs of a layer in one call: `blob_fwd` for u2_conv_fwd* with W[k] (Cs = Cin, Cd = Cout), `blob_dgrad` for the
+// input-gradient conv with W[k]^T (Cs = Cout, Cd = Cin); either may be NULL.  Each u2_conv_scratch_bytes(.) large.  The convs
+// then take W = NULL and the blob as `scratch`: weights are re-tiled once per optimizer step, not once per launch.
+extern "C" int u2_conv_pretile(const float *W, int32_t K, int32_t Cin, int32_t Cout, int32_t math, void *blob_fwd,
+                               void *blob_dgrad, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    U2_CHECK_ARG(math == U2_MATH_TF32 || math == U2_MATH_BF16, "u2_conv_pretile: math mode %d has no blobs", math);
+    if (blob_fwd && u2_conv_pretile_tc(W, 0, K, Cin, Cout, math, blob_fwd, (cudaStream_t)stream)) return 1;
+    if (blob_dgrad && u2_conv_pretile_tc(W, 1, K, Cout, Cin, math, blob_dgrad, (cudaStream_t)stream)) return 1;
+    return 0;
+#else
+    (void)W; (void)K; (void)Cin; (void)Cout; (void)math; (void)blob_fwd; (void)blob_dgrad; (void)stream;
+    u2_set_error("u2_conv_pretile: built without the tcgen05 path");
     return 1;
 #endif
 }

@@ -169,11 +169,12 @@ struct FwdParams {
     long long *dbg;  // optional per-CTA phase timestamps (U2_DEBUG_CONV_TIMING)
     int cp_mode;
     float *tile_stats;  // optional [tiles * 4][2][Cd]: per-warp column sums / sums of squares of Y (fused BatchNorm)
+    const float *Yadd;  // optional [n_dst, Cd]: added to the result in the epilogue (gradient of a second consumer of the input)
     int diag;  // U2_CONV_DIAG (timing diagnostics, results invalid): 1 = no weight loads, 2 = no gathers, 4 = gathers hit 128 hot rows
 };
 
 // ROWB = bytes of one gathered row per pipeline stage (128 or 64): 32/16 fp32 or 64/32 bf16 channels.
-template <int ROWB, bool BF16>
+template <int ROWB, bool BF16, bool YADD>
 __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParams p) {
     constexpr int ES = BF16 ? 2 : 4;          // element size
     constexpr int CHUNKS = ROWB / 16;         // 16-byte chunks per row per stage
@@ -347,6 +348,16 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             const int rsub = lane >> 3, cj = lane & 7;    // store phase: row within a group of 4, 16-byte chunk of the row
             for (int c0 = 0; c0 < NT; c0 += 32) {
                 const int ncol = min(32, NT - c0);        // 32, or 16 for the last chunk when NT % 32 == 16
+                // the addend rows of this chunk: all 8 loads of a lane in flight before the TMEM read and the staging
+                float4 ya[YADD ? 8 : 1];
+                if (YADD) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int dst = __shfl_sync(0xFFFFFFFFu, my_dst, 4 * i + rsub);
+                        ya[i] = (dst >= 0 && cj * 4 < ncol) ? __ldg(reinterpret_cast<const float4 *>(p.Yadd + (int64_t)dst * p.Cd + nt * NT + c0 + cj * 4))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 uint32_t v[32];
                 {
                     uint32_t lo[16], hi[16];
@@ -383,14 +394,23 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                         uint4 q;
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
                                      : "r"(stg_u32 + r * 128 + ((cj ^ (r & 7)) << 4)));
-                        *reinterpret_cast<uint4 *>(p.Y + (int64_t)dst * p.Cd + nt * NT + c0 + cj * 4) = q;
+                        const int64_t o = (int64_t)dst * p.Cd + nt * NT + c0 + cj * 4;
+                        if (YADD) {
+                            q.x = __float_as_uint(__uint_as_float(q.x) + ya[i].x);
+                            q.y = __float_as_uint(__uint_as_float(q.y) + ya[i].y);
+                            q.z = __float_as_uint(__uint_as_float(q.z) + ya[i].z);
+                            q.w = __float_as_uint(__uint_as_float(q.w) + ya[i].w);
+                        }
+                        *reinterpret_cast<uint4 *>(p.Y + o) = q;
                     }
                 }
             }
         } else {
             if (my_dst >= 0) {
                 float *yrow = p.Y + (int64_t)my_dst * p.Cd + nt * NT;
-                for (int c0 = 0; c0 < NT; c0 += 4) *reinterpret_cast<uint4 *>(yrow + c0) = make_uint4(0u, 0u, 0u, 0u);
+                const float *arow = YADD ? p.Yadd + (int64_t)my_dst * p.Cd + nt * NT : nullptr;
+                for (int c0 = 0; c0 < NT; c0 += 4)
+                    *reinterpret_cast<float4 *>(yrow + c0) = arow ? __ldg(reinterpret_cast<const float4 *>(arow + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (p.tile_stats) {
                 float *ts = p.tile_stats + ((size_t)blockIdx.x * 4 + warp) * 2 * p.Cd + nt * NT;
@@ -793,20 +813,20 @@ size_t u2_conv_tc_scratch_bytes(int64_t n_dst, int32_t K, int32_t Cs, int32_t Cd
     return (size_t)K * Cs * Cd * (math == U2_MATH_BF16 ? 2 : 4);
 }
 
-template <int ROWB, bool BF16>
-static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_t st) {
-    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int ROWB, bool BF16, bool YADD>
+static int launch_fwd_v2(const FwdParams &p, dim3 grid, size_t smem, cudaStream_t st) {
+    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16, YADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // the launcher sizes the stages for 2-3 co-resident CTAs: ask for the full shared-memory carve-out, otherwise the
     // driver may keep a larger L1 and fewer CTAs fit than planned
     static const int carve = getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared;
-    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<ROWB, BF16, YADD>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     if (getenv("U2_DEBUG_CONV_TIMING")) {
         int nb = 0, nb0 = 0, nb32 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_fwd_tc_kernel<ROWB, BF16>, NUM_THREADS, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, conv_fwd_tc_kernel<ROWB, BF16>, NUM_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb32, conv_fwd_tc_kernel<ROWB, BF16>, NUM_THREADS, 32768);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_fwd_tc_kernel<ROWB, BF16, YADD>, NUM_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, conv_fwd_tc_kernel<ROWB, BF16, YADD>, NUM_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb32, conv_fwd_tc_kernel<ROWB, BF16, YADD>, NUM_THREADS, 32768);
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, conv_fwd_tc_kernel<ROWB, BF16>);
+        cudaFuncGetAttributes(&fa, conv_fwd_tc_kernel<ROWB, BF16, YADD>);
         int smem_sm = 0, smem_blk = 0, regs_sm = 0;
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, 0);
         cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0);
@@ -816,9 +836,14 @@ static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_
                 nb, smem, nb0, nb32, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes,
                 fa.preferredShmemCarveout, smem_sm, smem_blk, regs_sm);
     }
-    conv_fwd_tc_kernel<ROWB, BF16><<<grid, NUM_THREADS, smem, st>>>(p);
+    conv_fwd_tc_kernel<ROWB, BF16, YADD><<<grid, NUM_THREADS, smem, st>>>(p);
     U2_LAUNCH_OK();
     return 0;
+}
+
+template <int ROWB, bool BF16>
+static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_t st) {
+    return p.Yadd ? launch_fwd_v2<ROWB, BF16, true>(p, grid, smem, st) : launch_fwd_v2<ROWB, BF16, false>(p, grid, smem, st);
 }
 
 // Host side of U2_DEBUG_CONV_TIMING: per-CTA clock64 stamps (16 slots per CTA) -> one summary line.
@@ -868,10 +893,37 @@ static void conv_dbg_report(const char *tag, const long long *d_dbg, size_t n_ct
     free(h);
 }
 
-// X: fp32 rows (math TF32) or bf16 rows (math BF16); W always the fp32 parameter tensor.
+// fp32 weights [K][Cs][Cd] (or [K][Cd][Cs] when w_transposed) -> the blob layout conv_fwd_tc_kernel streams
+int u2_conv_pretile_tc(const float *W, int32_t w_transposed, int32_t K, int32_t Cs, int32_t Cd, int32_t math, void *blob,
+                       cudaStream_t st) {
+    const bool bf16 = math == U2_MATH_BF16;
+    const int es = bf16 ? 2 : 4;
+    const int ROWB = pick_rowb(Cs, es), NT = pick_nt(Cd);
+    const int KC = ROWB ? ROWB / es : 0;
+    U2_CHECK_ARG(ROWB && NT && K <= 32, "u2_conv_pretile: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
+    U2_CHECK_ARG(W && blob && (((uintptr_t)W | (uintptr_t)blob) & 15) == 0, "u2_conv_pretile: null or misaligned pointer");
+    if (bf16) {
+        const int64_t total8 = (int64_t)K * Cs * Cd / 8;
+        if (w_transposed)
+            pretile_weights_bf16_kernel<true><<<(unsigned)u2_ceil_div(total8, 256), 256, 0, st>>>(W, (uint4 *)blob, K, Cs, Cd, KC, NT);
+        else
+            pretile_weights_bf16_kernel<false><<<(unsigned)u2_ceil_div(total8, 256), 256, 0, st>>>(W, (uint4 *)blob, K, Cs, Cd, KC, NT);
+    } else {
+        const int64_t total4 = (int64_t)K * Cs * Cd / 4;
+        if (w_transposed)
+            pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)blob, K, Cs, Cd, KC, NT);
+        else
+            pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)blob, K, Cs, Cd, KC, NT);
+    }
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+// X: fp32 rows (math TF32) or bf16 rows (math BF16); W the fp32 parameter tensor, or NULL when `scratch` already holds the
+// blob u2_conv_pretile_tc wrote for this (shape, direction, math).
 int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
-                   void *scratch, size_t scratch_bytes, float *tile_stats, cudaStream_t st) {
+                   void *scratch, size_t scratch_bytes, float *tile_stats, const float *Yadd, cudaStream_t st) {
     const bool bf16 = math == U2_MATH_BF16;
     const int es = bf16 ? 2 : 4;
     U2_CHECK_ARG(!tile_stats || pick_nt(Cd) % 32 == 0, "u2_conv_fwd_tc: fused column statistics need Cd tiles of 32 (Cd=%d)", Cd);
@@ -882,27 +934,16 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     U2_CHECK_ARG(ROWB && NT && K <= 32, "u2_conv_fwd_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
     U2_CHECK_ARG(ld % TILE_M == 0, "u2_conv_fwd_tc: table leading dimension must be a multiple of 128");
     U2_CHECK_ARG(scratch && scratch_bytes >= (size_t)K * Cs * Cd * es, "u2_conv_fwd_tc: scratch too small");
-    U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)scratch) & 15) == 0,
+    U2_CHECK_ARG((((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)scratch | (uintptr_t)Yadd) & 15) == 0,
                  "u2_conv_fwd_tc: pointers must be 16-byte aligned");
-    if (bf16) {
-        const int64_t total8 = (int64_t)K * Cs * Cd / 8;
-        if (w_transposed)
-            pretile_weights_bf16_kernel<true><<<(unsigned)u2_ceil_div(total8, 256), 256, 0, st>>>(W, (uint4 *)scratch, K, Cs, Cd, KC, NT);
-        else
-            pretile_weights_bf16_kernel<false><<<(unsigned)u2_ceil_div(total8, 256), 256, 0, st>>>(W, (uint4 *)scratch, K, Cs, Cd, KC, NT);
-    } else {
-        const int64_t total4 = (int64_t)K * Cs * Cd / 4;
-        if (w_transposed)
-            pretile_weights_kernel<true><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-        else
-            pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)scratch, K, Cs, Cd, KC, NT);
-    }
-    U2_LAUNCH_OK();
+    if (W && u2_conv_pretile_tc(W, w_transposed, K, Cs, Cd, math, scratch, st)) return 1;
+    (void)KC;
 
     FwdParams p;
     p.X = (const uint8_t *)X; p.Wt = (const uint8_t *)scratch; p.table = table; p.perm = perm; p.Y = Y;
     p.dbg = nullptr;
     p.tile_stats = tile_stats;
+    p.Yadd = Yadd;
     static const int cp_mode = getenv("U2_CPASYNC_MODE") ? atoi(getenv("U2_CPASYNC_MODE")) : 1;  // .ca measured 15-25 % faster
     p.cp_mode = cp_mode;
     const char *diag_env = getenv("U2_CONV_DIAG");  // read per call: scripts/diag_conv.py flips it between launches

@@ -66,13 +66,23 @@ def _is_sparse_conv(m) -> bool:
 
 
 def _residual_forward(block):
-    """forward of a ResidualBlock whose `net` ends in (Conv3d with a BatchNorm epilogue, absorbed BatchNorm)."""
+    """forward of a ResidualBlock whose `net` ends in (Conv3d with a BatchNorm epilogue, absorbed BatchNorm).
+    The block input feeds two consumers, net[0] and the shortcut.  When net[0] is a fused conv node the shortcut reads the
+    input through that node's alias output, so that in backward the shortcut's gradient arrives at the node and is added
+    inside its dgrad kernel instead of in a separate accumulation pass over the [N, C] gradient."""
     head, last_conv = list(block.net.children())[:-2], list(block.net.children())[-2]
+    first_fused = bool(head) and _is_sparse_conv(head[0]) and getattr(head[0], "_u2_epilogue", None) is not None
 
     def forward(x):
-        shortcut = block.downsample(x)
-        h = x
-        for m in head:
+        if first_fused:
+            h, alias = head[0](x, want_alias=True)
+            xa = type(x)(coords=x.coords, feats=alias, stride=x.stride)
+            xa.cmaps, xa.kmaps = x.cmaps, x.kmaps
+            shortcut = block.downsample(xa)
+            rest = head[1:]
+        else:
+            shortcut, h, rest = block.downsample(x), x, head
+        for m in rest:
             h = m(h)
         return last_conv(h, residual=shortcut.feats, relu=True)
 

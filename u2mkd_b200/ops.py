@@ -76,6 +76,22 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_workspaces = {}
+
+
+def _ws(name: str, nbytes: int, device) -> torch.Tensor:
+    """Cached scratch buffer (uint8, >= nbytes) for kernels that only need it while they run.  Reuse is ordered by the
+    stream: every user of one `name` launches on the same stream, so the next kernel that overwrites the buffer runs after
+    the previous reader (forward: the caller's stream; autograd replays backward on that stream too).  Side-stream users
+    pass their own name.  Saves ~350 torch.empty calls (1.5 ms of host time) per training step."""
+    key = (name, torch.device(device).index)
+    t = _workspaces.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = t
+    return t
+
+
 # -------------------------------------------------------------------------------- hashing
 def sphash(coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
     """spf.sphash (core/models/utils.py:19,43,49,86,92): int32 [N,4] (+[K,3]) -> int64 [N] / [K,N]."""
@@ -450,24 +466,29 @@ def _timed(kind, kmap, n_dst, K, c_src, c_dst, launch):
     conv_timer.record(kind, kmap, n_dst, K, c_src, c_dst, e0, e1)
 
 
-def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math, side=None):
+def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math, side=None, blob=None, yadd=None):
+    """One fused gather-GEMM launch.  `blob`: weights already re-tiled by u2_conv_pretile for this direction (then `w` is
+    not read); `yadd`: fp32 [n_dst, c_dst] added in the epilogue (sorted-tile path only)."""
     K, ld = table.shape
     n_src, c_src = x.shape
     y = torch.empty((n_dst, c_dst), dtype=torch.float32, device=x.device)
     assert (x.dtype == torch.bfloat16) == (math == MATH_BF16), (x.dtype, math)
-    sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
-    scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device) if sbytes else None
+    if blob is not None:
+        scratch, sbytes, wptr = blob, blob.numel(), None
+    else:
+        sbytes = lib().u2_conv_scratch_bytes(n_dst, K, c_src, c_dst, math)
+        scratch = _ws("pretile", sbytes, x.device) if sbytes else None
+        wptr = w.data_ptr()
     if side is not None and _state["sort_tiles"] and lib().u2_conv_tc_shape_supported(c_src, c_dst, K, math):
         tabP, perm, tmask = kmap.sorted_tables(side)
         _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd_perm(
-            x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), tabP.data_ptr(), perm.data_ptr(),
-            None, ld, n_dst, K, c_dst, y.data_ptr(), math, _ptr(scratch),
-            sbytes, _st())))
+            x.data_ptr(), n_src, c_src, wptr, int(w_transposed), tabP.data_ptr(), perm.data_ptr(), _ptr(yadd), ld, n_dst, K,
+            c_dst, y.data_ptr(), math, _ptr(scratch), sbytes, _st())))
         return y
     _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd(
-        x.data_ptr(), n_src, c_src, w.data_ptr(), int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
+        x.data_ptr(), n_src, c_src, wptr, int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
         math, _ptr(scratch), sbytes, _st())))
-    return y
+    return y if yadd is None else y.add_(yadd)
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -578,8 +599,8 @@ def flush_bn_counters() -> None:
 
 
 def _bn_scratch(c: int, device) -> torch.Tensor:
-    """Per-CTA partial sums of the two BatchNorm reductions (stream-ordered allocation from torch's pool)."""
-    return torch.empty(lib().u2_bn_scratch_bytes(c), dtype=torch.uint8, device=device)
+    """Per-CTA partial sums of the two BatchNorm reductions (consumed by the fold kernel of the same call)."""
+    return _ws("bn", lib().u2_bn_scratch_bytes(c), device)
 
 
 class BatchNormFn(Function):
@@ -649,14 +670,18 @@ def bf16_view(x: torch.Tensor) -> torch.Tensor:
 
 class ConvBNReLUFn(Function):
     """Sequential(Conv3d, BatchNorm[, ReLU]) of core/models/build_blocks.py:21-84 as one node (bf16 math):
-    forward : conv (epilogue leaves the column sums of Y) -> [all-reduce] -> normalise(+ReLU), fp32 + bf16 out
-    backward: BN reduce -> [all-reduce] -> BN dx written as bf16 only -> dgrad + wgrad
-    i.e. no statistics pass over Y, no cast pass before the next conv or before dgrad/wgrad, and the fp32
-    gradient of Y never exists."""
+    forward : weights re-tiled once for both directions -> conv (epilogue leaves the column sums of Y) -> [all-reduce]
+              -> normalise(+residual)(+ReLU), fp32 + bf16 out
+    backward: BN reduce -> [all-reduce] -> BN dx written as bf16 only -> dgrad (+ the gradient of the input's other
+              consumer, added in the conv epilogue) + wgrad
+    i.e. no statistics pass over Y, no cast pass before the next conv or before dgrad/wgrad, the fp32 gradient of Y never
+    exists, and no separate accumulation pass for an input that feeds this conv and a shortcut.
+    want_alias: also return the input `feats` as a third output; whatever consumes that alias (the ResidualBlock shortcut)
+    sends its gradient back through THIS node, where it is added inside the dgrad kernel."""
 
     @staticmethod
     def forward(ctx, feats, feats_bf16, weight, gamma, beta, residual, running_mean, running_var, momentum, eps, relu,
-                group, kmap: KernelMap, transposed: bool):
+                group, kmap: KernelMap, transposed: bool, want_alias: bool = False):
         K, cin, cout = weight.shape
         weight = weight.contiguous()
         if not transposed:
@@ -666,58 +691,69 @@ class ConvBNReLUFn(Function):
         dev = feats_bf16.device
         n_src = feats_bf16.shape[0]
         ld = table.shape[1]
+        st = _st()
+        l = lib()
         y = torch.empty((n_dst, cout), dtype=torch.float32, device=dev)
-        sbytes = lib().u2_conv_scratch_bytes(n_dst, K, cin, cout, MATH_BF16)
-        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        # both weight blobs now (W[k] for this conv, W[k]^T for its dgrad): the parameter does not change before backward
+        sbytes = l.u2_conv_scratch_bytes(n_dst, K, cin, cout, MATH_BF16)
+        need_dgrad = ctx.needs_input_grad[0]
+        blobs = torch.empty(2 * sbytes if need_dgrad else sbytes, dtype=torch.uint8, device=dev)
+        check(l.u2_conv_pretile(weight.data_ptr(), K, cin, cout, MATH_BF16, blobs.data_ptr(),
+                                blobs.data_ptr() + sbytes if need_dgrad else None, st))
         if _state["sort_tiles"]:
             tab, perm, _ = kmap.sorted_tables(side)
             rows = ld
         else:
             tab, perm, rows = table, None, n_dst
-        parts = lib().u2_conv_tile_stats_parts(rows)
-        tstats = torch.empty((parts, 2, cout), dtype=torch.float32, device=dev)
-        _timed("fwd", kmap, n_dst, K, cin, cout, lambda: check(lib().u2_conv_fwd_stats(
-            feats_bf16.data_ptr(), n_src, cin, weight.data_ptr(), 0, tab.data_ptr(), _ptr(perm), ld, n_dst, K, cout,
-            y.data_ptr(), MATH_BF16, scratch.data_ptr(), sbytes, tstats.data_ptr(), tstats.numel() * 4, _st())))
+        parts = l.u2_conv_tile_stats_parts(rows)
+        tstats = _ws("tstats", parts * 2 * cout * 4, dev)
+        _timed("fwd", kmap, n_dst, K, cin, cout, lambda: check(l.u2_conv_fwd_stats(
+            feats_bf16.data_ptr(), n_src, cin, None, 0, tab.data_ptr(), _ptr(perm), ld, n_dst, K, cout,
+            y.data_ptr(), MATH_BF16, blobs.data_ptr(), sbytes, tstats.data_ptr(), tstats.numel(), st)))
         sums = torch.empty(2 * cout + 1, dtype=torch.float64, device=dev)
-        check(lib().u2_bn_stats_from_tiles(tstats.data_ptr(), parts, cout, n_dst, sums.data_ptr(), _st()))
+        check(l.u2_bn_stats_from_tiles(tstats.data_ptr(), parts, cout, n_dst, sums.data_ptr(), st))
         if group is not None:
             torch.distributed.all_reduce(sums, group=group)
         z = torch.empty_like(y)
         zb = torch.empty((n_dst, cout), dtype=torch.bfloat16, device=dev)
-        mean = torch.empty(cout, dtype=torch.float32, device=dev)
-        invstd = torch.empty(cout, dtype=torch.float32, device=dev)
+        stats = torch.empty((2, cout), dtype=torch.float32, device=dev)  # saved mean, invstd
         if residual is not None:
             residual = residual.contiguous()
             assert residual.shape == y.shape and residual.dtype == torch.float32, (residual.shape, y.shape)
-        check(lib().u2_bn_apply_dual(y.data_ptr(), n_dst, cout, sums.data_ptr(), float(eps), float(momentum),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(residual), z.data_ptr(),
-                                     zb.data_ptr(), mean.data_ptr(), invstd.data_ptr(), _ptr(running_mean),
-                                     _ptr(running_var), _st()))
-        _count(5)
+        check(l.u2_bn_apply_dual(y.data_ptr(), n_dst, cout, sums.data_ptr(), float(eps), float(momentum),
+                                 gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(residual), z.data_ptr(),
+                                 zb.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * cout, _ptr(running_mean),
+                                 _ptr(running_var), st))
+        _count(6)
         # with a residual the ReLU mask cannot be recomputed from y alone: keep the output z for it
-        ctx.save_for_backward(feats_bf16, weight, y, gamma, beta, mean, invstd, sums,
-                              z if (residual is not None and relu) else None)
+        ctx.save_for_backward(feats_bf16, weight, y, gamma, beta, stats, sums,
+                              z if (residual is not None and relu) else None,
+                              blobs[sbytes:] if need_dgrad else None)
         ctx.misc = (kmap, transposed, relu, group, residual is not None)
         ctx.mark_non_differentiable(zb)
-        ctx.set_materialize_grads(False)  # no zero-filled "gradient" for the bf16 copy
+        ctx.set_materialize_grads(False)  # no zero-filled "gradient" for the bf16 copy / an unused alias
+        if want_alias:
+            return z, zb, feats
         return z, zb
 
     @staticmethod
-    def backward(ctx, dz, _dzb):
-        xb, weight, y, gamma, beta, mean, invstd, sums, zmask = ctx.saved_tensors
+    def backward(ctx, dz, _dzb, d_alias=None):
+        xb, weight, y, gamma, beta, stats, sums, zmask, blob_dgrad = ctx.saved_tensors
         kmap, transposed, relu, group, has_res = ctx.misc
+        n_ret = 15
         if dz is None:
-            return (None,) * 14
+            return (d_alias,) + (None,) * (n_ret - 1)
         dz = dz.contiguous().float()
         K, cin, cout = weight.shape
         n, c = y.shape
         dev = y.device
+        l = lib()
+        mean_p, invstd_p = stats.data_ptr(), stats.data_ptr() + 4 * c
         dsum = torch.empty(2 * c, dtype=torch.float64, device=dev)
         scratch = _bn_scratch(c, dev)
-        check(lib().u2_bn_bwd_reduce(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
-                                     gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(zmask), dsum.data_ptr(),
-                                     scratch.data_ptr(), scratch.numel(), _st()))
+        check(l.u2_bn_bwd_reduce(dz.data_ptr(), y.data_ptr(), n, c, mean_p, invstd_p,
+                                 gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(zmask), dsum.data_ptr(),
+                                 scratch.data_ptr(), scratch.numel(), _st()))
         dparam = dsum.float()
         dbeta, dgamma = dparam[:c], dparam[c:]
         if group is not None:
@@ -728,10 +764,10 @@ class ConvBNReLUFn(Function):
         if has_res and ctx.needs_input_grad[5]:
             # without a ReLU the residual's gradient is dz itself; with one, the masked dz written by the kernel
             dres = torch.empty_like(dz) if relu else dz
-        check(lib().u2_bn_bwd_apply_dual(dz.data_ptr(), y.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(),
-                                         gamma.data_ptr(), beta.data_ptr(), dsum.data_ptr(), sums.data_ptr() + 16 * c,
-                                         int(relu), _ptr(zmask), dres.data_ptr() if (dres is not None and relu) else None,
-                                         None, dyb.data_ptr(), _st()))
+        check(l.u2_bn_bwd_apply_dual(dz.data_ptr(), y.data_ptr(), n, c, mean_p, invstd_p,
+                                     gamma.data_ptr(), beta.data_ptr(), dsum.data_ptr(), sums.data_ptr() + 16 * c,
+                                     int(relu), _ptr(zmask), dres.data_ptr() if (dres is not None and relu) else None,
+                                     None, dyb.data_ptr(), _st()))
         _count(3)
         grad_feats = grad_weight = None
         # dgrad and wgrad only share their inputs.  On the coarse strides neither fills the 148 SMs (a few hundred CTAs),
@@ -746,7 +782,7 @@ class ConvBNReLUFn(Function):
             flat = kmap.flat_pairs
 
             def wgrad():
-                _timed("wgrad" + tag, kmap, n, K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                _timed("wgrad" + tag, kmap, n, K, cin, cout, lambda: check(l.u2_conv_wgrad_pairs(
                     xb.data_ptr(), cin, dyb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
                     flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, _st())))
 
@@ -758,11 +794,13 @@ class ConvBNReLUFn(Function):
                 wgrad()
         if ctx.needs_input_grad[0]:
             bwd_table = kmap.nbr if transposed else kmap.nbrT
+            if d_alias is not None:
+                d_alias = d_alias.contiguous().float()
             grad_feats = _conv_gather_gemm("dgrad" + tag, kmap, dyb, weight, True, bwd_table, xb.shape[0], cin, MATH_BF16,
-                                           side=not transposed)
+                                           side=not transposed, blob=blob_dgrad, yadd=d_alias)
         if side is not None:
             torch.cuda.current_stream(dev).wait_stream(side)
-        return (grad_feats, None, grad_weight, dgamma, dbeta, dres) + (None,) * 8
+        return (grad_feats, None, grad_weight, dgamma, dbeta, dres) + (None,) * (n_ret - 6)
 
 
 _side_streams = {}
@@ -791,9 +829,11 @@ def _bn_group(bn):
     return None
 
 
-def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, relu: bool, residual=None):
+def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, relu: bool, residual=None, want_alias=False):
     """conv3d -> bn [-> + residual] (-> relu) on feature matrices. Fused node where the bf16 tcgen05 kernels cover
-    the layer, otherwise the separate operators (same results up to summation order)."""
+    the layer, otherwise the separate operators (same results up to summation order).
+    want_alias: returns (out, alias) where alias is `feats` routed through the fused node — hand it to the input's other
+    consumer (the ResidualBlock shortcut) and its gradient is added inside this conv's dgrad kernel."""
     group = _bn_group(bn)
     K, cin, cout = weight.shape
     n_dst = kmap.n_in if transposed else kmap.n_out
@@ -807,18 +847,25 @@ def sparse_conv_bn_relu(feats, weight, kmap: KernelMap, transposed: bool, bn, re
              and (cout // ((cout + 255) // 256)) % 32 == 0)
     if not fused:
         if residual is None:
-            return batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, relu, group)
-        out = batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, False, group) + residual
-        return torch.relu_(out) if relu else out
+            out = batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, relu, group)
+        else:
+            out = batch_norm_relu(sparse_conv(feats, weight, kmap, transposed), bn, False, group) + residual
+            out = torch.relu_(out) if relu else out
+        return (out, feats) if want_alias else out
     momentum = float(bn.momentum)
     _count_batch(bn)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     feats = feats.contiguous()
-    z, zb = ConvBNReLUFn.apply(feats, bf16_view(feats), weight, bn.weight, bn.bias, residual, rm, rv, momentum, bn.eps,
-                               relu, group, kmap, transposed)
-    stash_bf16(z, zb)
-    return z
+    fb = bf16_view(feats)
+    use_alias = bool(want_alias and feats.requires_grad and _state.get("fuse_grad_add", True))
+    res = ConvBNReLUFn.apply(feats, fb, weight, bn.weight, bn.bias, residual, rm, rv, momentum, bn.eps,
+                             relu, group, kmap, transposed, use_alias)
+    stash_bf16(res[0], res[1])
+    if use_alias:
+        stash_bf16(res[2], fb)
+        return res[0], res[2]
+    return (res[0], feats) if want_alias else res[0]
 
 
 def _bn_momentum(bn) -> float:

@@ -35,13 +35,16 @@ def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1)
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, stride=1, dilation=1,
-           transposed: bool = False, epilogue=None, residual=None) -> SparseTensor:
+           transposed: bool = False, epilogue=None, residual=None, want_alias: bool = False) -> SparseTensor:
     """F.conv3d of torchsparse v1.4.0: kernel-map lookup/build, then
     one fused gather-GEMM kernel (ops.ConvolutionFn) instead of K gather/mm/scatter rounds.
     `epilogue=(bn_module, relu)` (set by u2mkd_b200.fusion.optimize, not part of the torchsparse signature)
     applies that BatchNorm(+ReLU) to the result inside the same autograd node; `residual` (a feature matrix,
-    only with an epilogue) is added between the BatchNorm and the ReLU (ResidualBlock tail)."""
+    only with an epilogue) is added between the BatchNorm and the ReLU (ResidualBlock tail).  want_alias (fusion only):
+    returns (output, alias) with alias = the input feature matrix routed through the fused conv node, see
+    ops.sparse_conv_bn_relu."""
     assert residual is None or epilogue is not None
+    alias = input.feats
     feats, coords = input.feats, input.coords
     kernel_size, stride, dilation = (make_ntuple(v, ndim=3) for v in (kernel_size, stride, dilation))
     unit = (1, 1, 1)
@@ -52,7 +55,9 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
             # BatchNorm epilogue fused like every other conv
             kmap = ops.identity_kernel_map(feats.shape[0], feats.device)
             if epilogue is not None and bias is None:
-                feats = ops.sparse_conv_bn_relu(feats, weight.unsqueeze(0), kmap, False, *epilogue, residual=residual)
+                res = ops.sparse_conv_bn_relu(feats, weight.unsqueeze(0), kmap, False, *epilogue, residual=residual,
+                                              want_alias=want_alias)
+                feats, alias = res if want_alias else (res, alias)
                 epilogue = None
             else:
                 feats = ops.sparse_conv(feats, weight.unsqueeze(0), kmap, transposed=False)
@@ -71,7 +76,8 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
         elif any(s > 1 for s in stride):
             coords = input.cmaps[out_stride]  # upstream skips this on a cache hit
         if epilogue is not None and bias is None:
-            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, False, *epilogue, residual=residual)
+            res = ops.sparse_conv_bn_relu(feats, weight, kmap, False, *epilogue, residual=residual, want_alias=want_alias)
+            feats, alias = res if want_alias else (res, alias)
             epilogue = None
         else:
             feats = ops.sparse_conv(feats, weight, kmap, transposed=False)
@@ -79,7 +85,8 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
         out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
         kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
         if epilogue is not None and bias is None:
-            feats = ops.sparse_conv_bn_relu(feats, weight, kmap, True, *epilogue, residual=residual)
+            res = ops.sparse_conv_bn_relu(feats, weight, kmap, True, *epilogue, residual=residual, want_alias=want_alias)
+            feats, alias = res if want_alias else (res, alias)
             epilogue = None
         else:
             feats = ops.sparse_conv(feats, weight, kmap, transposed=True)
@@ -96,4 +103,4 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
     output.cmaps = input.cmaps
     output.cmaps.setdefault(output.stride, output.coords)
     output.kmaps = input.kmaps
-    return output
+    return (output, alias) if want_alias else output

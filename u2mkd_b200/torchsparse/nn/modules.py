@@ -55,14 +55,16 @@ class Conv3d(nn.Module):
         if self.bias is not None:
             self.bias.data.uniform_(-std, std)
 
-    def forward(self, input: SparseTensor, residual=None, relu=None) -> SparseTensor:
-        """`residual` / `relu` are used by u2mkd_b200.fusion only (ResidualBlock tail folded into this conv's
-        BatchNorm epilogue); the torchsparse call signature is forward(input)."""
+    def forward(self, input: SparseTensor, residual=None, relu=None, want_alias=False) -> SparseTensor:
+        """`residual` / `relu` / `want_alias` are used by u2mkd_b200.fusion only (ResidualBlock tail folded into this
+        conv's BatchNorm epilogue, shortcut gradient folded into its dgrad); the torchsparse call signature is
+        forward(input)."""
         epilogue = getattr(self, "_u2_epilogue", None)
         if epilogue is not None and relu is not None:
             epilogue = (epilogue[0], bool(relu))
         return F.conv3d(input, self.kernel, kernel_size=self.kernel_size, bias=self.bias, stride=self.stride,
-                        dilation=self.dilation, transposed=self.transposed, epilogue=epilogue, residual=residual)
+                        dilation=self.dilation, transposed=self.transposed, epilogue=epilogue, residual=residual,
+                        want_alias=want_alias)
 
 
 class BatchNorm(nn.BatchNorm1d):
