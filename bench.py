@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size")
+    ap.add_argument("--grad-bf16", action="store_true",
+                    help="DDP communication hook: gradients cross NVLink as bf16 (halves the all-reduce bytes; off = the reference's fp32)")
     ap.add_argument("--no-fusion", action="store_true", help="keep torch BatchNorm/ReLU modules unfused")
     ap.add_argument("--overlap-rows", type=int, default=None,
                     help="run wgrad next to dgrad on a side stream for layers up to this many rows (default: all; 0 = off)")
@@ -271,6 +273,9 @@ def run_ours(args, w):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.bucket_mb)  # train_spformer.py:82-83
+        if args.grad_bf16:
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     # torch's single-pass multi-tensor SGD (same update rule as train_spformer.py's optimizer, one kernel per chunk)
     opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4,
                           fused=not args.no_fused_sgd)
@@ -413,6 +418,9 @@ def run_ours(args, w):
                            "scans_per_gpu": w["batch"], "voxels_per_step_rank0": int(np.mean([b[0].shape[0] for b in pool])),
                            "params": n_params, "optimizer": "sgd-nesterov", "loss": "cross_entropy",
                            "parallelism": f"dp{world}" + ("" if world == 1 or args.no_sync_bn else "+syncbn"),
+                           "syncbn_transport": (None if world == 1 or args.no_sync_bn else
+                                                ("nvlink peer memory" if any(v is not None for v in ops._exchanges.values()) else "nccl")),
+                           "grad_allreduce": None if world == 1 else ("bf16" if args.grad_bf16 else "fp32"),
                            "fused_bn_relu": not args.no_fusion,
                            "fused_conv_bn": not (args.no_fusion or args.no_conv_bn),
                            "fused_residual": not (args.no_fusion or args.no_conv_bn or args.no_residual_fusion),

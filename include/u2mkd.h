@@ -229,6 +229,17 @@ int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, 
 /* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
 int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);
 
+/* ---- SyncBatchNorm statistics exchange over NVLink peer memory: replaces the NCCL collectives torch SyncBatchNorm issues per
+ * layer and pass (core/models/utils.py:138-141, train_spformer.py:77-83) by one single-block kernel that pushes the local
+ * fp64 sums into every peer's mapped buffer, waits for the peers' flags and sums in rank order (all-reduce, in place).
+ * peer_bufs: HOST array [world] of device pointers, peer_bufs[r] = rank r's buffer (u2_syncbn_buffer_bytes() bytes,
+ * zero-filled once) as mapped into this process; seq = 1, 2, 3, ... identical on all ranks for the same exchange.        */
+size_t u2_syncbn_buffer_bytes(void);
+int32_t u2_syncbn_max_len(void);
+int32_t u2_syncbn_max_world(void);
+int u2_syncbn_exchange(double *vals, int32_t len, const void *const *peer_bufs, int32_t world, int32_t rank, uint64_t seq,
+                       u2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

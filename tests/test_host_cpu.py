@@ -42,10 +42,11 @@ def test_ctypes_signatures_match_the_header():
         t = " ".join(c_type.replace("const", " ").split())
         if "*" in t or t.startswith("u2_stream_t"):
             return "ptr"
-        return {"int64_t": "i64", "int32_t": "i32", "int": "i32", "float": "f32", "size_t": "size", "double": "f64"}[t]
+        return {"int64_t": "i64", "uint64_t": "size", "int32_t": "i32", "int": "i32", "float": "f32", "size_t": "size",
+                "double": "f64"}[t]
 
     ctk = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int64: "i64", ctypes.c_int32: "i32", ctypes.c_int: "i32",
-           ctypes.c_float: "f32", ctypes.c_size_t: "size", ctypes.c_double: "f64"}
+           ctypes.c_float: "f32", ctypes.c_size_t: "size", ctypes.c_double: "f64", ctypes.c_uint64: "size"}  # c_size_t is c_uint64 on LP64
     for name, (restype, argtypes) in _lib._SIGNATURES.items():
         ret, params = decls[name]
         params = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]

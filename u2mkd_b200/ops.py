@@ -576,6 +576,62 @@ def sparse_conv(feats, weight, kmap: KernelMap, transposed: bool = False, math: 
     return ConvolutionFn.apply(feats, weight, kmap, transposed, _state["math"] if math is None else math)
 
 
+# -------------------------------------------------------------------------------- SyncBatchNorm statistics exchange
+class _PeerExchange:
+    """All-reduce of the short fp64 statistics vectors of SyncBatchNorm over NVLink peer memory (csrc/syncbn.cu): torch
+    symmetric memory provides the mapped buffers, one single-block kernel per exchange does the rest (no NCCL launch)."""
+
+    def __init__(self, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(lib().u2_syncbn_buffer_bytes(), dtype=torch.uint8, device=dev)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.world, self.rank = int(self.handle.world_size), int(self.handle.rank)
+        if self.world > lib().u2_syncbn_max_world():
+            raise RuntimeError("group larger than the exchange buffer layout")
+        self.buf.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # every rank's flags are zero before anybody publishes
+        self.ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.seq = 0
+
+    def all_reduce_(self, vals: torch.Tensor) -> None:
+        assert vals.dtype == torch.float64 and vals.is_contiguous() and vals.numel() <= lib().u2_syncbn_max_len()
+        self.seq += 1
+        check(lib().u2_syncbn_exchange(vals.data_ptr(), vals.numel(), self.ptrs, self.world, self.rank, self.seq, _st()))
+        _count()
+
+
+_exchanges = {}
+
+
+def stats_all_reduce_(vals: torch.Tensor, group) -> None:
+    """Sum `vals` (fp64, short) over the ranks of `group`, in place: peer-memory exchange when the ranks share an NVLink
+    domain and torch symmetric memory is available (U2_SYNCBN_TRANSPORT=auto|peer|nccl), else one NCCL all-reduce."""
+    import os
+    import torch.distributed as dist
+    key = id(group)
+    ex = _exchanges.get(key, False)
+    if ex is False:
+        mode = os.environ.get("U2_SYNCBN_TRANSPORT", "auto")
+        ex = None
+        if mode != "nccl" and vals.is_cuda and dist.get_backend(group) == "nccl":
+            try:
+                ex = _PeerExchange(group)
+            except Exception as e:  # no symmetric memory on this system / group: the NCCL collective does the job
+                if mode == "peer":
+                    raise
+                ex = None
+                import warnings
+                warnings.warn(f"SyncBatchNorm peer-memory exchange unavailable ({e!r}); using NCCL all_reduce")
+        _exchanges[key] = ex
+    if ex is not None:
+        ex.all_reduce_(vals)
+    else:
+        dist.all_reduce(vals, group=group)
+
+
 # -------------------------------------------------------------------------------- batch norm (+ReLU)
 _pending_counters = []
 
@@ -617,7 +673,7 @@ class BatchNormFn(Function):
         scratch = _bn_scratch(c, x.device)
         check(lib().u2_bn_stats(x.data_ptr(), n, c, sums.data_ptr(), scratch.data_ptr(), scratch.numel(), st))
         if group is not None:
-            torch.distributed.all_reduce(sums, group=group)
+            stats_all_reduce_(sums, group)
         y = torch.empty_like(x)
         mean = torch.empty(c, dtype=torch.float32, device=x.device)
         invstd = torch.empty(c, dtype=torch.float32, device=x.device)
@@ -645,7 +701,7 @@ class BatchNormFn(Function):
         dbeta, dgamma = dparam[:c], dparam[c:]
         if group is not None:
             dsum = dsum.clone()
-            torch.distributed.all_reduce(dsum, group=group)
+            stats_all_reduce_(dsum, group)
         dx = torch.empty_like(x)
         check(lib().u2_bn_bwd_apply(dy.data_ptr(), x.data_ptr(), n, c, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                     beta.data_ptr(), dsum.data_ptr(), sums.data_ptr() + 16 * c, int(relu), dx.data_ptr(),
@@ -713,7 +769,7 @@ class ConvBNReLUFn(Function):
         sums = torch.empty(2 * cout + 1, dtype=torch.float64, device=dev)
         check(l.u2_bn_stats_from_tiles(tstats.data_ptr(), parts, cout, n_dst, sums.data_ptr(), st))
         if group is not None:
-            torch.distributed.all_reduce(sums, group=group)
+            stats_all_reduce_(sums, group)
         z = torch.empty_like(y)
         zb = torch.empty((n_dst, cout), dtype=torch.bfloat16, device=dev)
         stats = torch.empty((2, cout), dtype=torch.float32, device=dev)  # saved mean, invstd
@@ -758,7 +814,7 @@ class ConvBNReLUFn(Function):
         dbeta, dgamma = dparam[:c], dparam[c:]
         if group is not None:
             dsum = dsum.clone()
-            torch.distributed.all_reduce(dsum, group=group)
+            stats_all_reduce_(dsum, group)
         dyb = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
         dres = None
         if has_res and ctx.needs_input_grad[5]:
