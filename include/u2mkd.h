@@ -229,6 +229,14 @@ int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, 
 /* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
 int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);
 
+/* ---- index part of initial_voxelize in one call (core/models/utils.py:19-25): replaces sphash -> torch.unique ->
+ * sphashquery -> spcount -> round(spvoxelize(coords)).  coords int32 [n,4] (already floored) -> idx_query int64 [n],
+ * counts int32 (sized n, first n_vox valid), voxel_coords int32 [n,4] (first n_vox rows valid), n_vox_dev (device int64).
+ * Voxel v is the v-th smallest FNV key, i.e. the order torch.unique(pc_hash) gives the reference.                      */
+size_t u2_unique_voxelize_scratch_bytes(int64_t n);
+int u2_unique_voxelize(const int32_t *coords, int64_t n, int64_t *idx_query, int32_t *counts, int32_t *voxel_coords,
+                       int64_t *n_vox_dev, void *scratch, size_t scratch_bytes, u2_stream_t stream);
+
 /* ---- SyncBatchNorm statistics exchange over NVLink peer memory: replaces the NCCL collectives torch SyncBatchNorm issues per
  * layer and pass (core/models/utils.py:138-141, train_spformer.py:77-83) by one single-block kernel that pushes the local
  * fp64 sums into every peer's mapped buffer, waits for the peers' flags and sums in rank order (all-reduce, in place).

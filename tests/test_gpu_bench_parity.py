@@ -133,3 +133,21 @@ def test_voxel_to_point_nearest(oracle, cuda_lib, stride):
     oo.F.backward(gr)
     og.F.backward(gr.cuda())
     assert float((fg.grad.cpu() - fo.grad).abs().max()) <= 1e-4 * float(fo.grad.abs().max())
+
+
+@pytest.mark.parametrize("n,extent", [(1, 4), (5000, 12), (200000, 90)])
+def test_unique_voxelize_matches_reference_sequence(oracle, cuda_lib, n, extent):
+    """u2_unique_voxelize against the five reference operators it replaces (core/models/utils.py:19-25), with several
+    points per voxel: idx_query, counts and voxel coordinates bit-exact, same voxel order (ascending FNV hash)."""
+    from u2mkd_b200 import ops
+    rng = np.random.default_rng(n)
+    c = torch.from_numpy(np.concatenate([rng.integers(0, extent, (n, 3)), rng.integers(0, 3, (n, 1))], 1).astype(np.int32))
+    h = oracle.sphash(c)
+    u = torch.unique(h)
+    idx = oracle.sphashquery(h, u)
+    cnt = oracle.spcount(idx.int(), len(u))
+    vc = torch.round(oracle.spvoxelize(c.float(), idx, cnt)).int()
+    g_idx, g_cnt, g_vc = ops.unique_voxelize(c.cuda())
+    assert g_idx.dtype == torch.int64 and g_cnt.dtype == torch.int32 and g_vc.dtype == torch.int32
+    assert torch.equal(g_idx.cpu(), idx) and torch.equal(g_cnt.cpu(), cnt) and torch.equal(g_vc.cpu(), vc)
+    assert int(g_cnt.sum()) == n and (n < 1000 or int(g_cnt.max()) > 1)

@@ -88,6 +88,94 @@ extern "C" int u2_downsample_coords(const int32_t *coords, int64_t n, int32_t sx
     return 0;
 }
 
+// ------------------------------------------------------------------ initial voxelisation (index part)
+// core/models/utils.py:19-25: pc_hash = sphash(floor(coords)); sparse_hash = torch.unique(pc_hash);
+// idx_query = sphashquery(pc_hash, sparse_hash); counts = spcount(idx_query, len(sparse_hash));
+// coords = round(spvoxelize(floored, idx_query, counts)) — five operators, a sort inside torch.unique, a hash table
+// built only to be queried once, and a scatter-mean of integers whose result is the integer itself.  One call here:
+// FNV key per point -> radix sort of (key, point) -> run heads -> exclusive scan = voxel id (ascending key: the
+// reference's voxel order) -> idx_query / counts / voxel coordinates scattered from the sorted runs.
+__global__ void __launch_bounds__(256) uv_key_kernel(const int4 *__restrict__ coords, int64_t n, unsigned long long *__restrict__ keys,
+                                                     int *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = __ldg(coords + i);
+    keys[i] = (unsigned long long)u2_fnv4(c.x, c.y, c.z, c.w);
+    idx[i] = (int)i;
+}
+
+__global__ void __launch_bounds__(256) uv_head_kernel(const unsigned long long *__restrict__ keys, int64_t n, int *__restrict__ head) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// vid = inclusive scan of the run heads (1-based voxel id of every sorted position)
+__global__ void __launch_bounds__(256) uv_scatter_kernel(const int4 *__restrict__ coords, const int *__restrict__ idx_sorted,
+                                                         const int *__restrict__ head, const int *__restrict__ vid, int64_t n,
+                                                         int64_t *__restrict__ idx_query, int *__restrict__ counts,
+                                                         int4 *__restrict__ voxel_coords, int64_t *__restrict__ n_vox) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int v = vid[j] - 1, pt = idx_sorted[j];
+    idx_query[pt] = v;
+    if (head[j]) {
+        voxel_coords[v] = __ldg(coords + pt);
+        // run length = distance to the next head: the sorted positions of a voxel are contiguous
+        int64_t e = j + 1;
+        while (e < n && !head[e]) e++;
+        counts[v] = (int)(e - j);
+    }
+    if (j == n - 1) *n_vox = (int64_t)v + 1;
+}
+
+static size_t uv_cub_bytes(int64_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (const int *)nullptr,
+                                    (int *)nullptr, n, 0, 60);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (const int *)nullptr, (int *)nullptr, n);
+    return align_up(a > b ? a : b);
+}
+
+extern "C" size_t u2_unique_voxelize_scratch_bytes(int64_t n) {
+    if (n <= 0) n = 1;
+    return 2 * align_up((size_t)n * 8) + 4 * align_up((size_t)n * 4) + uv_cub_bytes(n);
+}
+
+// coords int32 [n,4] (already floored) -> idx_query int64 [n], counts int32 [>= n_vox] (caller sizes it n), voxel_coords
+// int32 [>= n_vox, 4], n_vox (device int64).  Voxel v = the v-th smallest FNV key, as torch.unique orders them.
+extern "C" int u2_unique_voxelize(const int32_t *coords, int64_t n, int64_t *idx_query, int32_t *counts, int32_t *voxel_coords,
+                                  int64_t *n_vox_dev, void *scratch, size_t scratch_bytes, u2_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    U2_CHECK_ARG(scratch_bytes >= u2_unique_voxelize_scratch_bytes(n), "u2_unique_voxelize: scratch too small");
+    U2_CHECK_ARG((((uintptr_t)coords | (uintptr_t)voxel_coords | (uintptr_t)scratch) & 15) == 0,
+                 "u2_unique_voxelize: pointers must be 16-byte aligned");
+    U2_CHECK_ARG(n < 0x7FFFFFFFLL, "u2_unique_voxelize: too many points for int32 row indices");
+    if (n == 0) {
+        U2_CUDA_OK(cudaMemsetAsync(n_vox_dev, 0, 8, st));
+        return 0;
+    }
+    char *p = (char *)scratch;
+    unsigned long long *keys_a = (unsigned long long *)p; p += align_up((size_t)n * 8);
+    unsigned long long *keys_b = (unsigned long long *)p; p += align_up((size_t)n * 8);
+    int *idx_a = (int *)p; p += align_up((size_t)n * 4);
+    int *idx_b = (int *)p; p += align_up((size_t)n * 4);
+    int *head = (int *)p; p += align_up((size_t)n * 4);
+    int *vid = (int *)p; p += align_up((size_t)n * 4);
+    size_t cub_bytes = uv_cub_bytes(n);
+    const unsigned grid = (unsigned)u2_ceil_div(n, 256);
+    uv_key_kernel<<<grid, 256, 0, st>>>((const int4 *)coords, n, keys_a, idx_a);
+    U2_LAUNCH_OK();
+    U2_CUDA_OK(cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 60, st));
+    uv_head_kernel<<<grid, 256, 0, st>>>(keys_b, n, head);
+    U2_LAUNCH_OK();
+    U2_CUDA_OK(cub::DeviceScan::InclusiveSum(p, cub_bytes, head, vid, n, st));
+    uv_scatter_kernel<<<grid, 256, 0, st>>>((const int4 *)coords, idx_b, head, vid, n, idx_query, counts, (int4 *)voxel_coords,
+                                            n_vox_dev);
+    U2_LAUNCH_OK();
+    return 0;
+}
+
 // ------------------------------------------------------------------ kernel map
 __global__ void __launch_bounds__(256) coord_insert_kernel(const int4 *__restrict__ coords, int64_t n, U2Slot *table,
                                                            unsigned long long mask) {

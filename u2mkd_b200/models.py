@@ -36,11 +36,16 @@ def build_family(ts) -> SimpleNamespace:
         """utils.py:15-35 — quantise, hash, unique, scatter-mean coords + features."""
         new_float_coord = torch.cat([(z.C[:, :3] * init_res) / after_res, z.C[:, -1].view(-1, 1)], 1)
         floored = torch.floor(new_float_coord)
-        pc_hash = spf.sphash(floored.int())
-        sparse_hash = torch.unique(pc_hash)
-        idx_query = spf.sphashquery(pc_hash, sparse_hash)
-        counts = spf.spcount(idx_query.int(), len(sparse_hash))
-        coords = torch.round(spf.spvoxelize(floored, idx_query, counts)).int()
+        fused = getattr(spf, "unique_voxelize", None)
+        if fused is not None and floored.is_cuda:
+            # product path: the five index operators below as one call (same voxel order, same idx_query / counts / coords)
+            idx_query, counts, coords = fused(floored.int())
+        else:
+            pc_hash = spf.sphash(floored.int())
+            sparse_hash = torch.unique(pc_hash)
+            idx_query = spf.sphashquery(pc_hash, sparse_hash)
+            counts = spf.spcount(idx_query.int(), len(sparse_hash))
+            coords = torch.round(spf.spvoxelize(floored, idx_query, counts)).int()
         feats = spf.spvoxelize(z.F, idx_query, counts)
         x = SparseTensor(feats, coords, 1)
         x.cmaps.setdefault(x.stride, x.coords)

@@ -144,6 +144,28 @@ def spcount(coords: torch.Tensor, num: int) -> torch.Tensor:
     return out
 
 
+def unique_voxelize(coords: torch.Tensor):
+    """Index part of initial_voxelize (core/models/utils.py:19-25) in one call: int32 [N,4] floored coordinates ->
+    (idx_query int64 [N], counts int32 [n_vox], voxel_coords int32 [n_vox,4]); voxel order = ascending FNV hash, exactly
+    what torch.unique(sphash(coords)) gives the reference.  One host sync (the voxel count sizes every later tensor)."""
+    _need_cuda(coords)
+    assert coords.dtype == torch.int and coords.ndim == 2 and coords.shape[1] == 4, (coords.dtype, coords.shape)
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    dev = coords.device
+    idx_query = torch.empty(n, dtype=torch.int64, device=dev)
+    counts = torch.empty(n, dtype=torch.int, device=dev)
+    vox = torch.empty((n, 4), dtype=torch.int, device=dev)
+    n_vox = torch.empty(1, dtype=torch.int64, device=dev)
+    sbytes = lib().u2_unique_voxelize_scratch_bytes(n)
+    scratch = _ws("uvox", sbytes, dev)
+    check(lib().u2_unique_voxelize(coords.data_ptr(), n, idx_query.data_ptr(), counts.data_ptr(), vox.data_ptr(),
+                                   n_vox.data_ptr(), scratch.data_ptr(), scratch.numel(), _st()))
+    _count(5)
+    m = int(n_vox.item())
+    return idx_query, counts[:m], vox[:m]
+
+
 # -------------------------------------------------------------------------------- voxelize
 class VoxelizeFn(Function):
     """spf.spvoxelize (core/models/utils.py:24,26,58): scatter-mean with autograd."""
