@@ -229,6 +229,15 @@ int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, 
 /* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
 int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);
 
+/* ---- coordinate table of one coordinate set, built once per tensor stride and shared by the kernel maps and the
+ * point<->voxel index queries of that stride (replaces the per-call table inside [TS nn/functional/query.py]
+ * sphashquery, call sites core/models/utils.py:50,93).  table: u2_hash_table_bytes(n) bytes.  u2_coord_table_query:
+ * out int64 [K, nq], out[k][i] = row of (q[i] + offsets[k]) or -1; offsets int32 [K,3] device (NULL with K = 1).
+ * u2_kmap_build accepts such a table as `scratch` with scratch_bytes = 0.                                               */
+int u2_coord_table_build(const int32_t *coords, int64_t n, void *table, size_t table_bytes, u2_stream_t stream);
+int u2_coord_table_query(const void *table, size_t table_bytes, const int32_t *qcoords, int64_t nq, const int32_t *offsets,
+                         int32_t K, int64_t *out, u2_stream_t stream);
+
 /* ---- index part of initial_voxelize in one call (core/models/utils.py:19-25): replaces sphash -> torch.unique ->
  * sphashquery -> spcount -> round(spvoxelize(coords)).  coords int32 [n,4] (already floored) -> idx_query int64 [n],
  * counts int32 (sized n, first n_vox valid), voxel_coords int32 [n,4] (first n_vox rows valid), n_vox_dev (device int64).

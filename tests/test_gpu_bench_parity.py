@@ -151,3 +151,25 @@ def test_unique_voxelize_matches_reference_sequence(oracle, cuda_lib, n, extent)
     assert g_idx.dtype == torch.int64 and g_cnt.dtype == torch.int32 and g_vc.dtype == torch.int32
     assert torch.equal(g_idx.cpu(), idx) and torch.equal(g_cnt.cpu(), cnt) and torch.equal(g_vc.cpu(), vc)
     assert int(g_cnt.sum()) == n and (n < 1000 or int(g_cnt.max()) > 1)
+
+
+@pytest.mark.parametrize("stride", [1, 4])
+def test_coord_query_matches_hash_query_composition(oracle, cuda_lib, stride):
+    """ops.coord_query (cached per-stride coordinate table, offsets applied on the fly) against the reference
+    composition sphashquery(sphash(q[, offsets]), sphash(ref)) (core/models/utils.py:49-50, 86-93): bit-exact."""
+    from u2mkd_b200 import ops
+    rng = np.random.default_rng(stride)
+    ref = np.unique(np.concatenate([rng.integers(0, 30, (20000, 3)) * stride, rng.integers(0, 2, (20000, 1))], 1).astype(np.int32), axis=0)
+    rng.shuffle(ref)
+    ref = torch.from_numpy(np.ascontiguousarray(ref))
+    q = torch.from_numpy(np.concatenate([rng.integers(-1, 31, (50000, 3)) * stride, rng.integers(0, 2, (50000, 1))], 1).astype(np.int32))
+    off = oracle.get_kernel_offsets(2, stride, 1)
+    want1 = oracle.sphashquery(oracle.sphash(q), oracle.sphash(ref))
+    want8 = oracle.sphashquery(oracle.sphash(q, off), oracle.sphash(ref))
+    refg = ref.cuda()
+    got1 = ops.coord_query(q.cuda(), refg)
+    got8 = ops.coord_query(q.cuda(), refg, off.cuda())
+    assert got1.shape == want1.shape and torch.equal(got1.cpu(), want1)
+    assert got8.shape == want8.shape == (8, 50000) and torch.equal(got8.cpu(), want8)
+    assert getattr(refg, "_u2_table", None) is not None  # the second query reused the first one's table
+    assert int((want1 >= 0).sum()) > 1000 and int((want1 < 0).sum()) > 1000

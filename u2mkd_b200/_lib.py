@@ -82,6 +82,8 @@ _SIGNATURES = {
     "u2_kmap_sort_scratch_bytes": (_sz, [_i64]),
     "u2_kmap_sort_rows": (ctypes.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "u2_conv_fwd_perm": (ctypes.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _sz, _p]),
+    "u2_coord_table_build": (ctypes.c_int, [_p, _i64, _p, _sz, _p]),
+    "u2_coord_table_query": (ctypes.c_int, [_p, _sz, _p, _i64, _p, _i32, _p, _p]),
     "u2_unique_voxelize_scratch_bytes": (_sz, [_i64]),
     "u2_unique_voxelize": (ctypes.c_int, [_p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "u2_syncbn_buffer_bytes": (_sz, []),

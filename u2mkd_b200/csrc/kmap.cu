@@ -220,10 +220,61 @@ __global__ void __launch_bounds__(256) kmap_query_kernel(const U2Slot *__restric
 
 extern "C" size_t u2_kmap_scratch_bytes(int64_t n_in) { return u2_hash_table_bytes(n_in); }
 
+// Coordinate table of one coordinate set (key = the reference's FNV hash of the row, value = row index): built ONCE per
+// tensor stride and shared by the kernel maps, point_to_voxel and voxel_to_point of that stride (the reference rebuilds a
+// cuckoo table inside every sphashquery call, 16 x per forward).
+extern "C" int u2_coord_table_build(const int32_t *coords, int64_t n, void *table, size_t table_bytes, u2_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    U2_CHECK_ARG(table && table_bytes >= u2_hash_table_bytes(n), "u2_coord_table_build: table too small");
+    U2_CHECK_ARG((((uintptr_t)coords | (uintptr_t)table) & 15) == 0, "u2_coord_table_build: pointers must be 16-byte aligned");
+    U2_CHECK_ARG(n < 0x7FFFFFFFLL, "u2_coord_table_build: too many rows");
+    const size_t tbytes = u2_hash_table_bytes(n);
+    U2_CUDA_OK(cudaMemsetAsync(table, 0xFF, tbytes, st));
+    if (n > 0) {
+        coord_insert_kernel<<<(unsigned)u2_ceil_div(n, 256), 256, 0, st>>>((const int4 *)coords, n, (U2Slot *)table,
+                                                                          tbytes / sizeof(U2Slot) - 1);
+        U2_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// out[k * nq + i] = row of (q[i].xyz + offsets[k], q[i].b) in the table's coordinate set, -1 if absent (K = 1, offsets =
+// NULL: the plain lookup of point_to_voxel; K = 8: the corner lookup of voxel_to_point, core/models/utils.py:84-93 —
+// sphash with offsets + sphashquery without the [K, N] int64 hash tensor in between).
+__global__ void __launch_bounds__(256) coord_query_kernel(const U2Slot *__restrict__ table, unsigned long long mask,
+                                                          const int4 *__restrict__ q, int64_t nq, const int *__restrict__ offsets,
+                                                          int K, int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int4 c = __ldg(q + i);
+    for (int k = 0; k < K; k++) {
+        const int ox = offsets ? __ldg(offsets + 3 * k) : 0, oy = offsets ? __ldg(offsets + 3 * k + 1) : 0,
+                  oz = offsets ? __ldg(offsets + 3 * k + 2) : 0;
+        out[(int64_t)k * nq + i] = (int64_t)u2_table_lookup(table, mask, (unsigned long long)u2_fnv4(c.x + ox, c.y + oy, c.z + oz, c.w));
+    }
+}
+
+extern "C" int u2_coord_table_query(const void *table, size_t table_bytes, const int32_t *qcoords, int64_t nq,
+                                    const int32_t *offsets, int32_t K, int64_t *out, u2_stream_t stream) {
+    if (nq == 0) return 0;
+    U2_CHECK_ARG(table && qcoords && out && K >= 1, "u2_coord_table_query: bad arguments");
+    const size_t cap = table_bytes / sizeof(U2Slot);
+    U2_CHECK_ARG(cap >= 1024 && (cap & (cap - 1)) == 0, "u2_coord_table_query: table_bytes %zu is not a table size", table_bytes);
+    U2_CHECK_ARG(((uintptr_t)qcoords & 15) == 0, "u2_coord_table_query: coordinates must be 16-byte aligned");
+    coord_query_kernel<<<(unsigned)u2_ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>((const U2Slot *)table, cap - 1,
+                                                                                         (const int4 *)qcoords, nq, offsets, K, out);
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+// scratch_bytes == 0: `scratch` is a coordinate table of in_coords that u2_coord_table_build already filled
+// (u2_hash_table_bytes(n_in) bytes); otherwise it is built here.
 extern "C" int u2_kmap_build(const int32_t *in_coords, int64_t n_in, const int32_t *out_coords, int64_t n_out,
                              const int32_t *offsets, int32_t K, int32_t *nbr, int64_t ld_out, int32_t *nbrT, int64_t ld_in,
                              int32_t *nbsizes, void *scratch, size_t scratch_bytes, u2_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    const bool prebuilt = scratch_bytes == 0 && scratch != nullptr;
+    if (prebuilt) scratch_bytes = u2_kmap_scratch_bytes(n_in);
     U2_CHECK_ARG(K > 0 && K <= 1024, "u2_kmap_build: bad K=%d", K);
     U2_CHECK_ARG(ld_out >= n_out && ld_in >= n_in, "u2_kmap_build: leading dimensions too small");
     U2_CHECK_ARG(scratch_bytes >= u2_kmap_scratch_bytes(n_in), "u2_kmap_build: scratch too small");
@@ -234,12 +285,14 @@ extern "C" int u2_kmap_build(const int32_t *in_coords, int64_t n_in, const int32
     if (ld_in > 0) U2_CUDA_OK(cudaMemsetAsync(nbrT, 0xFF, (size_t)K * ld_in * sizeof(int), st));
     if (ld_out == 0) return 0;
     const size_t tbytes = u2_hash_table_bytes(n_in);
-    U2_CUDA_OK(cudaMemsetAsync(scratch, 0xFF, tbytes, st));
     const unsigned long long mask = tbytes / sizeof(U2Slot) - 1;
-    if (n_in > 0) {
-        coord_insert_kernel<<<(unsigned)u2_ceil_div(n_in, 256), 256, 0, st>>>((const int4 *)in_coords, n_in,
-                                                                            (U2Slot *)scratch, mask);
-        U2_LAUNCH_OK();
+    if (!prebuilt) {
+        U2_CUDA_OK(cudaMemsetAsync(scratch, 0xFF, tbytes, st));
+        if (n_in > 0) {
+            coord_insert_kernel<<<(unsigned)u2_ceil_div(n_in, 256), 256, 0, st>>>((const int4 *)in_coords, n_in,
+                                                                                (U2Slot *)scratch, mask);
+            U2_LAUNCH_OK();
+        }
     }
     const int64_t row_blocks = u2_ceil_div(ld_out, 256);
     int slices = 1;

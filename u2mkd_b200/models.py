@@ -26,6 +26,7 @@ def build_family(ts) -> SimpleNamespace:
     spnn, spf = ts.nn, ts.nn.functional
     SparseTensor, PointTensor = ts.SparseTensor, ts.PointTensor
     get_kernel_offsets = ts.nn.utils.get_kernel_offsets
+    coord_query = getattr(spf, "coord_query", None)  # product-only fast path (cached per-stride coordinate table)
 
     # ------------------------------------------------------------------ point <-> voxel
     def _floor_to_stride(z, s):
@@ -58,7 +59,10 @@ def build_family(ts) -> SimpleNamespace:
         """utils.py:40-65 — scatter-mean point features into the voxels of x (cached per stride)."""
         cache = z.additional_features
         if cache is None or cache.get("idx_query") is None or cache["idx_query"].get(x.s) is None:
-            idx_query = spf.sphashquery(spf.sphash(_floor_to_stride(z, x.s[0])), spf.sphash(x.C))
+            if coord_query is not None and x.C.is_cuda:  # product path: one lookup kernel on the stride's cached table
+                idx_query = coord_query(_floor_to_stride(z, x.s[0]), x.C)
+            else:
+                idx_query = spf.sphashquery(spf.sphash(_floor_to_stride(z, x.s[0])), spf.sphash(x.C))
             counts = spf.spcount(idx_query.int(), x.C.shape[0])
             cache["idx_query"][x.s] = idx_query
             cache["counts"][x.s] = counts
@@ -73,8 +77,11 @@ def build_family(ts) -> SimpleNamespace:
         """utils.py:70-118 — trilinear devoxelise of x onto the points of z (cached per stride)."""
         if z.idx_query is None or z.weights is None or z.idx_query.get(x.s) is None or z.weights.get(x.s) is None:
             off = get_kernel_offsets(2, x.s, 1, device=z.F.device)
-            old_hash = spf.sphash(_floor_to_stride(z, x.s[0]), off)
-            idx_query = spf.sphashquery(old_hash, spf.sphash(x.C.to(z.F.device)))
+            if coord_query is not None and x.C.is_cuda and z.F.is_cuda:
+                idx_query = coord_query(_floor_to_stride(z, x.s[0]), x.C, off)
+            else:
+                old_hash = spf.sphash(_floor_to_stride(z, x.s[0]), off)
+                idx_query = spf.sphashquery(old_hash, spf.sphash(x.C.to(z.F.device)))
             weights = spf.calc_ti_weights(z.C, idx_query, scale=x.s[0]).transpose(0, 1).contiguous()
             idx_query = idx_query.transpose(0, 1).contiguous()
             if nearest:

@@ -144,6 +144,43 @@ def spcount(coords: torch.Tensor, num: int) -> torch.Tensor:
     return out
 
 
+def coord_table(coords: torch.Tensor) -> torch.Tensor:
+    """Hash table of a coordinate set (int32 [n,4] -> row index), cached on the tensor: one build per tensor stride
+    serves the kernel maps, point_to_voxel and voxel_to_point of that stride (the coordinate tensors are shared through
+    SparseTensor.cmaps, so the cache follows them)."""
+    _need_cuda(coords)
+    assert coords.dtype == torch.int and coords.ndim == 2 and coords.shape[1] == 4 and coords.is_contiguous()
+    st = getattr(coords, "_u2_table", None)
+    if st is not None and st[1] == coords._version and st[2] == coords.data_ptr():
+        return st[0]
+    n = coords.shape[0]
+    tbytes = lib().u2_hash_table_bytes(n)
+    table = torch.empty(tbytes, dtype=torch.uint8, device=coords.device)
+    check(lib().u2_coord_table_build(coords.data_ptr(), n, table.data_ptr(), tbytes, _st()))
+    _count(2)
+    coords._u2_table = (table, coords._version, coords.data_ptr())
+    return table
+
+
+def coord_query(queries: torch.Tensor, ref_coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row of every query coordinate (+ each of the K offsets) in ref_coords, -1 if absent: int64 [N] / [K, N].  Same
+    result as spf.sphashquery(spf.sphash(queries[, offsets]), spf.sphash(ref_coords)) (core/models/utils.py:49-50,86-93)
+    without the intermediate hash tensors and with the cached table of ref_coords."""
+    _need_cuda(queries, ref_coords, offsets)
+    assert queries.dtype == torch.int and queries.ndim == 2 and queries.shape[1] == 4
+    queries = queries.contiguous()
+    table = coord_table(ref_coords.contiguous() if not ref_coords.is_contiguous() else ref_coords)
+    n = queries.shape[0]
+    K = 1 if offsets is None else offsets.shape[0]
+    if offsets is not None:
+        offsets = offsets.contiguous().int()
+    out = torch.empty((K, n) if offsets is not None else (n,), dtype=torch.int64, device=queries.device)
+    check(lib().u2_coord_table_query(table.data_ptr(), table.numel(), queries.data_ptr(), n, _ptr(offsets), K, out.data_ptr(),
+                                     _st()))
+    _count()
+    return out
+
+
 def unique_voxelize(coords: torch.Tensor):
     """Index part of initial_voxelize (core/models/utils.py:19-25) in one call: int32 [N,4] floored coordinates ->
     (idx_query int64 [N], counts int32 [n_vox], voxel_coords int32 [n_vox,4]); voxel order = ascending FNV hash, exactly
@@ -396,12 +433,11 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets:
     nbr = torch.empty((K, ld_out), dtype=torch.int, device=dev)
     nbrT = torch.empty((K, ld_in), dtype=torch.int, device=dev)
     nbsizes = torch.empty(K, dtype=torch.int, device=dev)
-    sbytes = lib().u2_kmap_scratch_bytes(n_in)
-    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    table = coord_table(in_coords)  # built once per coordinate set (scratch_bytes = 0: pre-built table)
     check(lib().u2_kmap_build(in_coords.data_ptr(), n_in, out_coords.data_ptr(), n_out, offsets.data_ptr(), K,
-                              nbr.data_ptr(), ld_out, nbrT.data_ptr(), ld_in, nbsizes.data_ptr(), scratch.data_ptr(),
-                              sbytes, _st()))
-    _count(2)
+                              nbr.data_ptr(), ld_out, nbrT.data_ptr(), ld_in, nbsizes.data_ptr(), table.data_ptr(),
+                              0, _st()))
+    _count(1)
     return KernelMap(nbr, nbrT, nbsizes, n_in, n_out, offsets_host, same)
 
 

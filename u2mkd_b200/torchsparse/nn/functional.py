@@ -6,13 +6,13 @@ import functools
 import torch
 
 from ... import ops
-from ...ops import calc_ti_weights, spcount, spdevoxelize, sphash, sphashquery, spvoxelize, unique_voxelize
+from ...ops import calc_ti_weights, coord_query, spcount, spdevoxelize, sphash, sphashquery, spvoxelize, unique_voxelize
 from ..tensor import SparseTensor
 from ..utils import make_ntuple
 from .utils import get_kernel_offsets, kernel_offsets_host
 
 __all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "spdownsample",
-           "conv3d", "unique_voxelize"]
+           "conv3d", "unique_voxelize", "coord_query"]
 
 
 def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1) -> torch.Tensor:
