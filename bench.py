@@ -115,15 +115,20 @@ class ConvTimer:
         self.items.append((kind, kmap.nbsizes, n_dst, K, c_src, c_dst, e0, e1))
 
     def by_shape(self, steps):
-        """ms per step grouped by (kind, K, c_src, c_dst, n_dst): where the conv time goes."""
-        out = {}
+        """per (kind, K, c_src, c_dst): launches per step, average rows, ms per launch, ms per step, TFLOP/s over real pairs."""
+        out, pairs_cache = {}, {}
         for kind, nbsizes, n_dst, K, cs, cd, e0, e1 in self.items:
-            d = out.setdefault((kind, K, cs, cd, n_dst), [0, 0.0])
+            key = id(nbsizes)
+            if key not in pairs_cache:
+                pairs_cache[key] = int(nbsizes.sum().item())
+            d = out.setdefault((kind, K, cs, cd), [0, 0.0, 0, 0.0])
             d[0] += 1
             d[1] += e0.elapsed_time(e1)
+            d[2] += n_dst
+            d[3] += 2.0 * pairs_cache[key] * cs * cd
         rows = sorted(out.items(), key=lambda kv: -kv[1][1])
-        return [f"{k[0]:6s} K={k[1]:2d} {k[2]:4d}->{k[3]:4d} n_dst={k[4]:7d} x{v[0] // steps:3d}/step {v[1] / steps:7.3f} ms/step"
-                for k, v in rows]
+        return [f"{k[0]:6s} K={k[1]:2d} {k[2]:4d}->{k[3]:4d} x{v[0] / steps:5.1f}/step rows {v[2] // v[0]:7d}  {v[1] / v[0]:7.4f} ms/launch "
+                f"{v[1] / steps:7.3f} ms/step {v[3] / v[1] / 1e9:7.1f} TFLOP/s" for k, v in rows]
 
     def summary(self):
         """per kind: launches, total ms, algorithmic flops (2*M*Cs*Cd over REAL pairs only)."""
@@ -410,7 +415,7 @@ def run_ours(args, w):
                                  for k, d in summ.items()},
                     "conv_share_of_step": tot_ms / ms_instr}
         if os.environ.get("U2_BENCH_LAYERS"):
-            print("\n".join(timer.by_shape(args.steps)[:40]), file=sys.stderr)
+            print("\n".join(timer.by_shape(args.steps)), file=sys.stderr)
         line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": math, "data": "synthetic",

@@ -71,9 +71,9 @@ def launches(path):
             f.write(f"| `{k}` | {a[0]} | {a[1] / 1e6:.3f} | {100 * a[1] / tot:.1f}% | {a[2] / a[0] / 1e6:.2f} |\n")
     traffic = {k: {"launches": a[0], "dram_bytes_per_launch": a[2] / a[0], "ms_total": a[1] / 1e6, "share": a[1] / tot}
                for k, a in agg.items() if k.startswith("conv_")}
-    json.dump({"source": os.path.basename(path), "note": "ncu launch list of `bench.py --steps 1 --warmup 1 --quick --pool 2`",
-               "kernels": traffic}, open(os.path.join(OUT, "r1_conv_traffic.json"), "w"), indent=1)
-    print("wrote", tag + "_by_kernel.md", "and r1_conv_traffic.json")
+    json.dump({"source": os.path.basename(path), "note": "ncu launch list of a short bench.py run",
+               "kernels": traffic}, open(os.path.join(OUT, tag.split("_")[0] + "_conv_traffic.json"), "w"), indent=1)
+    print("wrote", tag + "_by_kernel.md", "and", tag.split("_")[0] + "_conv_traffic.json")
     return agg
 
 
