@@ -352,7 +352,16 @@ int main(int argc, char **argv) {
     }
     unsigned long long *sink;
     CK(cudaMalloc(&sink, 8));
-    for (int pitch : {128}) {
+    // argv[1]: comma-separated methods (default 0,4,5,9,12,13,14); argv[2]: comma-separated row pitches in bytes (default 128,384)
+    bool want[16] = {};
+    std::vector<int> pitches;
+    {
+        const char *ms = argc > 1 ? argv[1] : "0,4,5,9,12,13,14";
+        for (const char *c = ms; *c;) { int m = atoi(c); if (m >= 0 && m < 16) want[m] = true; while (*c && *c != ',') c++; if (*c) c++; }
+        const char *ps = argc > 2 ? argv[2] : "128,384";
+        for (const char *c = ps; *c;) { pitches.push_back(atoi(c)); while (*c && *c != ',') c++; if (*c) c++; }
+    }
+    for (int pitch : pitches) {
         const int slices = pitch / 128;
         uint8_t *X;
         CK(cudaMalloc(&X, (size_t)n * pitch));
@@ -388,15 +397,14 @@ int main(int argc, char **argv) {
                 long long real_rows = 0;
                 for (int v : idx) real_rows += v >= 0;
                 for (int method = 0; method <= 14; method++) {
-                    if (method == 12 || method == 13 || method == 5) continue;
-                    if ((method >= 1 && method <= 4) || method == 6 || method == 7 || method == 9 || method == 11 || method == 10 || method == 8) continue;  // measured: slower than 0 / 5 (see profiles/r2_gather_microbench.md)
+                    if (!want[method]) continue;
                     if ((method == 5 || method == 8) && !encode) continue;
                     if (method == 9 && pitch == 128) continue;
                     for (int W : {4, 8}) {
                         if (method == 5 && W < 4) continue;
                         if ((method == 4 || method == 9 || method == 14) && W != 4) continue;
                         for (int ctas : {1, 2, 3, 4}) {
-                            for (int S : {2}) {
+                            for (int S : {2, 4, 6}) {
                                 if (ctas * (W + 1) > 64 || (size_t)ctas * (S * STAGE + 3072) > 226 * 1024) continue;
                                 if (method == 3 && W == 4) continue;  // 32 rows per thread would not fit the register array
                                 Params p;

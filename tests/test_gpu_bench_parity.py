@@ -173,3 +173,41 @@ def test_coord_query_matches_hash_query_composition(oracle, cuda_lib, stride):
     assert got8.shape == want8.shape == (8, 50000) and torch.equal(got8.cpu(), want8)
     assert getattr(refg, "_u2_table", None) is not None  # the second query reused the first one's table
     assert int((want1 >= 0).sum()) > 1000 and int((want1 < 0).sum()) > 1000
+
+
+def test_prebuilt_kernel_maps_do_not_change_the_model(cuda_lib):
+    """ops.prebuild_maps: the kernel maps recorded during a first (lazy) forward pass are rebuilt right after
+    initial_voxelize on the next pass, so that no host synchronisation is left between the convs.  Same maps, same order
+    of arithmetic: logits and gradients identical to the lazy pass, and no map is built inside a conv any more."""
+    from u2mkd_b200 import models, ops, scans
+    import u2mkd_b200.torchsparse as ts
+    from u2mkd_b200.torchsparse.nn import functional as F
+    ops.set_math("fp32")
+    ops.set_prebuild(False)
+    ops.set_prebuild(True)          # empty plan
+    coords, feats = scans.make_batch([3], "nusc", 1, 0.2)
+    c, f = torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()
+    torch.manual_seed(0)
+    net = models.product().SPVCNN(cr=0.5, pres=0.2, vres=0.2, num_classes=17).cuda()
+    net.dropout = torch.nn.Identity()
+
+    def run():
+        net.zero_grad()
+        out = net({"lidar": ts.SparseTensor(f, c)})["x_vox"]
+        out.square().mean().backward()
+        return out.detach().clone(), net.stem[0].kernel.grad.detach().clone()
+
+    lazy = run()
+    assert len(ops._plan) >= 9, ops._plan.keys()   # 5 strides of k3 maps + 4 k2s2 maps
+    assert any("sortF" in v or "flat" in v or not v for v in ops._plan.values())
+    built = []
+    orig = F.prebuild_maps
+    F.prebuild_maps = lambda x: built.append(orig(x))
+    try:
+        pre = run()
+    finally:
+        F.prebuild_maps = orig
+    assert built == [len(ops._plan)], (built, len(ops._plan))   # every map of the second pass was built up front
+    assert torch.equal(lazy[0], pre[0])
+    # (the FFMA wgrad kernel accumulates with atomics: gradients agree to rounding, not bitwise)
+    assert float((lazy[1] - pre[1]).abs().max()) <= 1e-5 * float(lazy[1].abs().max())

@@ -128,6 +128,30 @@ def test_sorted_tiles_do_not_change_results(tc, oracle):
     assert torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("math,n,cin,cout", [("bf16", 40000, 64, 64), ("bf16", 30000, 192, 192), ("bf16", 9000, 512, 512),
+                                              ("tf32", 20000, 96, 48), ("bf16", 300, 128, 256)])
+def test_persistent_conv_kernel_matches_default(tc, monkeypatch, math, n, cin, cout):
+    """U2_CONV_KERNEL=ps (persistent warp-specialised schedule, kept as a measured alternative) issues the same MMAs in
+    the same order as the default kernel: bitwise identical outputs and input gradients, several tiles per CTA included."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin)
+    c = rand_coords(rng, n, extent=60).cuda()
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32)).cuda()
+    conv = gts.nn.Conv3d(cin, cout, 3).cuda()
+    tc.set_math(math)
+    outs = []
+    for kern in ("default", "ps"):
+        if kern == "ps":
+            monkeypatch.setenv("U2_CONV_KERNEL", "ps")
+        x = gts.SparseTensor(f.clone().requires_grad_(True), c)
+        y = conv(x)
+        y.F.square().sum().backward()
+        outs.append((y.F.detach().clone(), x.F.grad.clone()))
+    monkeypatch.delenv("U2_CONV_KERNEL")
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("n,cin,cout,ks,stride", [
     (6000, 64, 64, 3, 1), (3000, 96, 64, 3, 1), (2000, 128, 256, 3, 1), (4000, 64, 128, 2, 2), (1500, 512, 512, 3, 1),
     (3000, 192, 384, 3, 1), (129, 64, 64, 3, 1), (2500, 32, 32, 3, 1), (700, 768, 512, 3, 1)])

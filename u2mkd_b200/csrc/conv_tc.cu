@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "u2_common.cuh"
 
@@ -119,6 +120,38 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
     if (BF16) umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
     else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
 }
+// Warp-converged variants: ALL 32 lanes execute the statement with identical operands and elect.sync picks the issuing
+// lane inside the same asm block.  With `if (lane == 0) tcgen05.mma ...` the compiler treats the descriptors as per-thread
+// values and wraps every UTCHMMA / UTCBAR in a "waterfall" loop (ELECT + 4 R2UR.BROADCAST + BRA.U.ANY): measured ~75 cycles
+// per MMA and ~300 per commit on the issuing thread, i.e. ~600 cycles per 4-MMA work item before any tensor work — the
+// MMA thread, not the tensor pipe, paced the kernels (profiles/r2_conv_phase_clocks.md).
+template <bool BF16>
+__device__ __forceinline__ void umma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (BF16)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -170,6 +203,7 @@ struct FwdParams {
     int cp_mode;
     float *tile_stats;  // optional [tiles * 4][2][Cd]: per-warp column sums / sums of squares of Y (fused BatchNorm)
     const float *Yadd;  // optional [n_dst, Cd]: added to the result in the epilogue (gradient of a second consumer of the input)
+    int64_t n_tiles;  // persistent kernel: 128-row tiles to walk
     int diag;  // U2_CONV_DIAG (timing diagnostics, results invalid): 1 = no weight loads, 2 = no gathers, 4 = gathers hit 128 hot rows
 };
 
@@ -273,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         const int chunk = tid % CHUNKS, grp = tid / CHUNKS;
         int s = 0;
         uint32_t ph = 0;
-        long long dbg_wait = 0;
+        long long dbg_wait = 0, dbg_ph[3] = {0, 0, 0};
         for (uint32_t m = kmask; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
             const int cnt = s_cnt[k];
@@ -302,6 +336,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                 } else {
                     mbar_wait(s_empty + s, ph ^ 1u);
                 }
+                const long long tp0 = (dbg && tid == 0) ? clock64() : 0;
                 const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
                 const uint32_t stale = s_dirty[s * 4 + warp] & ~pm;
                 if (stale) {  // warp-uniform
@@ -315,13 +350,16 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
                 }
                 __syncwarp();
                 if (lane == 0) s_dirty[s * 4 + warp] = pm;
+                const long long tp1 = (dbg && tid == 0) ? clock64() : 0;
 #pragma unroll
                 for (int i = 0; i < CHUNKS; i++) {
                     if (i * ROWS_PER_IT + (warp * 32) / CHUNKS < cnt) {  // warp-uniform: this round has rows for this warp
                         if (off[i] != 0xFFFFFFFFu && !(p.diag & 2)) cp_async16_ca(a_base + dsto[i], xc + off[i]);
                     }
                 }
+                const long long tp2 = (dbg && tid == 0) ? clock64() : 0;
                 cp_async_mbar_arrive_noinc(s_full + s);
+                if (dbg && tid == 0) { const long long tp3 = clock64(); dbg_ph[0] += tp1 - tp0; dbg_ph[1] += tp2 - tp1; dbg_ph[2] += tp3 - tp2; }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -331,7 +369,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         // BatchNorm column sums are read from the same staging tile.  (The fp32 output write is ~25 % of the kernel on the
         // stride-1 layers, U2_CONV_DIAG=16, and it is the HBM traffic itself: storing straight from the TMEM registers,
         // 32 rows per instruction, takes the same time.)
-        if (dbg && tid == 0) { dbg[2] = clock64(); dbg[8] = dbg_wait; }
+        if (dbg && tid == 0) { dbg[2] = clock64(); dbg[8] = dbg_wait; dbg[10] = dbg_ph[0]; dbg[11] = dbg_ph[1]; dbg[12] = dbg_ph[2]; }
         const int64_t trow = row0 + warp * 32 + lane;
         int64_t row = trow;
         if (p.perm) row = __ldg(p.perm + trow);
@@ -443,7 +481,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
         const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, NT) : make_idesc_tf32(TILE_M, NT);
         int s = 0;
         uint32_t ph = 0;
-        long long dbg_wait_full = 0;
+        long long dbg_wait_full = 0, dbg_mma[3] = {0, 0, 0};
         for (int it = 0; it < n_items; it++) {
             if (dbg && lane == 0) {
                 const long long t0 = clock64();
@@ -452,30 +490,439 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_fwd_tc_kernel(const FwdParam
             } else {
                 mbar_wait(s_full + s, ph);
             }
+            const long long tm0 = (dbg && lane == 0) ? clock64() : 0;
             tc_fence_after();
             proxy_fence_async();
-            if (lane == 0) {
+            if (dbg && lane == 0) dbg_mma[0] += clock64() - tm0;
+            {   // all 32 lanes, converged: uniform descriptors, elect.sync inside the asm (see umma_elect)
+                const long long tm1 = dbg ? clock64() : 0;
                 const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
                 const uint32_t b_base = a_base + A_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < ROWB / 32; kk++) {  // one MMA consumes 32 bytes of K: 8 tf32 or 16 bf16
                     const uint64_t ad = make_smem_desc(a_base + kk * 2 * A_LBO, A_LBO, 128);
                     const uint64_t bd = make_smem_desc(b_base + kk * 2 * B_LBO, B_LBO, 128);
-                    umma<BF16>(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    umma_elect<BF16>(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                 }
-                umma_commit(s_empty + s);
-                if (it == n_items - 1) umma_commit(s_accum);
+                const long long tm2 = dbg ? clock64() : 0;
+                umma_commit_elect(s_empty + s);
+                if (it == n_items - 1) umma_commit_elect(s_accum);
+                if (dbg && lane == 0) { dbg_mma[1] += tm2 - tm1; dbg_mma[2] += clock64() - tm2; }
             }
-            __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        if (dbg && lane == 0) dbg[9] = dbg_wait_full;
+        if (dbg && lane == 0) { dbg[9] = dbg_wait_full; dbg[13] = dbg_mma[0]; dbg[14] = dbg_mma[1]; dbg[15] = dbg_mma[2]; }
     }
     if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     if (dbg && tid == 160) { dbg[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
+}
+
+// ------------------------------------------------------------------ fwd / dgrad, persistent warp-specialised kernel
+// Same math and shared-memory operand layouts as conv_fwd_tc_kernel above, different schedule.  What the phase clocks
+// of that kernel showed (profiles/r2_conv_phase_clocks.md): with 2-3 co-resident CTAs of 2 stages each, a work item
+// costs ~1400 cycles per CTA even with every global load switched off — all four producer warps walk through every
+// item (wait, clear stale rows, proxy fence, issue, arrive: ~900 dependent cycles each), the single MMA thread spends
+// ~650 cycles per item in fences / issue / commit, and with two stages neither side has slack.  Here:
+//   * ONE CTA per SM, persistent over (row tile, channel tile) work units, all of shared memory in one deep ring
+//     (3-8 stages) instead of 2-3 shallow ones;
+//   * a work item belongs to ONE producer warp (item g -> stage g % S -> warp g % S): the per-item fixed cost is paid by
+//     one warp while seven others are busy with the neighbouring items;
+//   * the accumulator is double-buffered in TMEM (2 x NT columns): four dedicated warps drain tile t while the
+//     producers and the MMA thread are already in tile t + 1; the neighbour table / row lists of tile t + 1 are built by
+//     two dedicated warps into the second table buffer meanwhile.
+constexpr int PS_MAX_STAGES = 8;
+constexpr int PS_PRODUCERS = 8;       // warps 8..15
+constexpr int PS_THREADS = 512;       // warps 0-3 epilogue, 4 MMA, 5 weights, 6-7 tables, 8-15 gather
+
+struct PsTab {   // byte offsets inside one table buffer
+    int tab, list, pm, cnt, kmask, bytes;
+};
+__host__ __device__ inline PsTab ps_tab_layout(int K) {
+    PsTab t;
+    t.tab = 0;
+    t.list = t.tab + K * TILE_M * 4;
+    t.pm = t.list + K * TILE_M;
+    t.cnt = t.pm + K * 16;
+    t.kmask = t.cnt + K * 4;
+    t.bytes = (t.kmask + 16 + 127) / 128 * 128;
+    return t;
+}
+
+template <int ROWB, bool BF16, bool YADD>
+__global__ void __launch_bounds__(PS_THREADS, 1) conv_fwd_ps_kernel(const FwdParams p) {
+    constexpr int ES = BF16 ? 2 : 4;
+    constexpr int CHUNKS = ROWB / 16;             // 16-byte chunks per row per stage
+    constexpr int RPI = 32 / CHUNKS;              // rows per warp-level LDGSTS
+    constexpr int A_BYTES = CHUNKS * A_LBO;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int NT = p.NT, S = p.stages;
+    const int B_LBO = NT * 16;
+    const int B_BYTES = CHUNKS * B_LBO;
+    const int stage_bytes = A_BYTES + B_BYTES;
+    const PsTab TL = ps_tab_layout(p.K);
+    uint8_t *s_stage = smem;
+    uint8_t *s_stg = smem + (size_t)S * stage_bytes;                 // 4 x 4 KB epilogue staging
+    uint8_t *s_tabs = s_stg + 4 * 4096;                              // 2 table buffers
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_tabs + 2 * TL.bytes);
+    uint64_t *s_empty = s_full + PS_MAX_STAGES;
+    uint64_t *s_tab_full = s_empty + PS_MAX_STAGES;                  // [2]
+    uint64_t *s_tab_empty = s_tab_full + 2;                          // [2]
+    uint64_t *s_acc_full = s_tab_empty + 2;                          // [2]
+    uint64_t *s_acc_empty = s_acc_full + 2;                          // [2]
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_acc_empty + 2);
+    int *s_acc_items = reinterpret_cast<int *>(s_tmem + 1);          // [2] items accumulated into buffer a (0: nothing)
+    uint32_t *s_dirty = reinterpret_cast<uint32_t *>(s_acc_items + 2);  // [PS_MAX_STAGES][4] rows of a stage that hold data
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_cc = p.Cs * ES / ROWB;
+    const int n_nt = p.Cd / NT;
+    const int64_t n_work = p.n_tiles * n_nt;
+    // producer warp w owns stage w: the items of one stage are filled by one warp in program order, so a parity wait on the
+    // stage's barriers can never be satisfied by a phase two uses back (a warp running ahead on a shared stage could)
+    const int n_prod = S < PS_PRODUCERS ? S : PS_PRODUCERS;
+
+    if (tid < PS_MAX_STAGES * 4) s_dirty[tid] = 0xFFFFFFFFu;  // a stage starts with stale shared memory in every row
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(s_full + s, 32 + 2);    // 32 cp.async completions of the owning warp + its release arrive + the weight thread
+            mbar_init(s_empty + s, 1);        // tcgen05.commit
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(s_tab_full + b, 2);                    // the two table warps
+            mbar_init(s_tab_empty + b, n_prod + 2);          // active producer warps + weight thread + MMA warp
+            mbar_init(s_acc_full + b, 1);                    // tcgen05.commit (or a plain arrive for an empty tile)
+            mbar_init(s_acc_empty + b, 4);                   // the four epilogue warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    // optional phase clocks (U2_DEBUG_CONV_TIMING=2): 32 slots per CTA
+    //  0 start, 1 end | MMA thread: 2 items, 3 wait full, 4 fences, 5 issue, 6 commit, 7 wait tab/acc
+    //  producer warp 0: 8 items, 9 wait empty, 10 zero + fence, 11 gather issue, 12 arrive, 13 wait table
+    //  epilogue warp 0: 14 wait acc_full, 15 work | table warp 0: 16 wait, 17 work | 18 tiles of this CTA
+    long long *dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 32 : nullptr;
+    if (dbg && tid == 0) dbg[0] = clock64();
+#define DBG_T() (dbg ? clock64() : 0LL)
+
+    if (warp >= 8) {
+        // ============================ A producers: one warp per work item ============================
+        const int pw = warp - 8;
+        const int chunk = lane % CHUNKS, grp = lane / CHUNKS;
+        uint32_t g = 0;  // running item number of this CTA (same sequence in every role)
+        int i = 0;
+        for (int64_t w = pw < n_prod ? (int64_t)blockIdx.x : n_work; w < n_work; w += gridDim.x, i++) {
+            const int b = i & 1;
+            const uint8_t *tb = s_tabs + b * TL.bytes;
+            const long long tq0 = DBG_T();
+            mbar_wait(s_tab_full + b, (uint32_t)(i >> 1) & 1u);
+            if (dbg && warp == 8 && lane == 0) dbg[13] += clock64() - tq0;
+            const int *s_tab = reinterpret_cast<const int *>(tb + TL.tab);
+            const uint8_t *s_list = tb + TL.list;
+            const uint32_t *s_pm = reinterpret_cast<const uint32_t *>(tb + TL.pm);
+            const int *s_cnt = reinterpret_cast<const int *>(tb + TL.cnt);
+            const uint32_t *km = reinterpret_cast<const uint32_t *>(tb + TL.kmask);
+            const uint32_t kmask = km[0] | km[1];
+            for (uint32_t m = kmask; m; m &= m - 1) {
+                const int k = __ffs(m) - 1;
+                for (int cc = 0; cc < n_cc; cc++, g++) {
+                    const int s = (int)(g % (uint32_t)S);
+                    if (s != pw) continue;
+                    const uint32_t ph = (g / (uint32_t)S) & 1u;
+                    const long long tp0 = DBG_T();
+                    mbar_wait(s_empty + s, ph ^ 1u);
+                    const long long tp1 = DBG_T();
+                    const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
+                    // rows that still hold the previous item's data but have no neighbour at this offset -> zero
+                    uint32_t any_stale = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t pmq = s_pm[k * 4 + q];
+                        const uint32_t stale = s_dirty[s * 4 + q] & ~pmq;
+                        any_stale |= stale;
+                        if ((stale >> lane) & 1u) {
+#pragma unroll
+                            for (int c = 0; c < CHUNKS; c++)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + c * A_LBO + (q * 32 + lane) * 16), "r"(0)
+                                             : "memory");
+                        }
+                    }
+                    if (any_stale) proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                    __syncwarp();
+                    if (lane < 4) s_dirty[s * 4 + lane] = s_pm[k * 4 + lane];
+                    const long long tp2 = DBG_T();
+                    // gather the present rows, RPI per instruction (lane group `grp` takes present row r * RPI + grp)
+                    const int cnt = s_cnt[k];
+                    const uint8_t *xc = p.X + (size_t)cc * ROWB + chunk * 16;
+                    const uint32_t dst0 = a_base + chunk * A_LBO;
+                    if (!(p.diag & 2)) {
+                        for (int j0 = 0; j0 < cnt; j0 += 4 * RPI) {
+                            int slot[4], src[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int j = j0 + u * RPI + grp;
+                                slot[u] = j < cnt ? (int)s_list[k * TILE_M + j] : -1;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) src[u] = slot[u] >= 0 ? s_tab[k * TILE_M + slot[u]] : 0;
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                if (slot[u] >= 0) cp_async16_ca(dst0 + slot[u] * 16, xc + (size_t)(uint32_t)src[u] * (uint32_t)(p.Cs * ES));
+                        }
+                    }
+                    const long long tp3 = DBG_T();
+                    cp_async_mbar_arrive_noinc(s_full + s);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_full + s);  // release: the s_dirty update and the zeroing stores of this warp
+                    if (dbg && warp == 8 && lane == 0) {
+                        dbg[8] += 1; dbg[9] += tp1 - tp0; dbg[10] += tp2 - tp1; dbg[11] += tp3 - tp2; dbg[12] += clock64() - tp3;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tab_empty + b);
+        }
+    } else if (warp == 6 || warp == 7) {
+        // ============================ table warps: neighbour table of the next tile -> shared memory ============================
+        const int tw = warp - 6;
+        int i = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, i++) {
+            const int b = i & 1;
+            uint8_t *tb = s_tabs + b * TL.bytes;
+            const long long tt0 = DBG_T();
+            if (i >= 2) mbar_wait(s_tab_empty + b, (uint32_t)((i >> 1) - 1) & 1u);
+            const long long tt1 = DBG_T();
+            int *s_tab = reinterpret_cast<int *>(tb + TL.tab);
+            uint8_t *s_list = tb + TL.list;
+            uint32_t *s_pm = reinterpret_cast<uint32_t *>(tb + TL.pm);
+            int *s_cnt = reinterpret_cast<int *>(tb + TL.cnt);
+            uint32_t *km = reinterpret_cast<uint32_t *>(tb + TL.kmask);
+            const int64_t row0 = (w / n_nt) * TILE_M;
+            uint32_t kmask = 0;
+            // offsets tw, tw + 2, ...; 7 offsets (28 loads per lane) in flight at a time
+            for (int k0 = tw; k0 < p.K; k0 += 14) {
+                int v[7][4];
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const int k = k0 + 2 * j;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) v[j][q] = k < p.K ? __ldg(p.table + (int64_t)k * p.ld + row0 + lane + 32 * q) : -1;
+                }
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const int k = k0 + 2 * j;
+                    if (k < p.K) {
+                        int cnt = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            s_tab[k * TILE_M + lane + 32 * q] = v[j][q];
+                            const uint32_t bal = __ballot_sync(0xffffffffu, v[j][q] >= 0);
+                            if (v[j][q] >= 0) s_list[k * TILE_M + cnt + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * q);
+                            if (lane == 0) s_pm[k * 4 + q] = bal;
+                            cnt += __popc(bal);
+                        }
+                        if (lane == 0) s_cnt[k] = cnt;
+                        if (cnt) kmask |= 1u << k;
+                    }
+                }
+            }
+            if (lane == 0) km[tw] = kmask;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tab_full + b);
+            if (dbg && tw == 0 && lane == 0) { dbg[16] += tt1 - tt0; dbg[17] += clock64() - tt1; dbg[18] += 1; }
+        }
+    } else if (warp == 5) {
+        // ============================ B producer: pre-tiled weight blobs, one bulk copy per item ============================
+        if (lane == 0) {
+            uint32_t g = 0;
+            int i = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, i++) {
+                const int b = i & 1;
+                const int nt = (int)(w % n_nt);
+                mbar_wait(s_tab_full + b, (uint32_t)(i >> 1) & 1u);
+                const uint32_t *km = reinterpret_cast<const uint32_t *>(s_tabs + b * TL.bytes + TL.kmask);
+                const uint32_t kmask = km[0] | km[1];
+                for (uint32_t m = kmask; m; m &= m - 1) {
+                    const int k = __ffs(m) - 1;
+                    for (int cc = 0; cc < n_cc; cc++, g++) {
+                        const int s = (int)(g % (uint32_t)S);
+                        const uint32_t ph = (g / (uint32_t)S) & 1u;
+                        mbar_wait(s_empty + s, ph ^ 1u);
+                        const uint32_t b_base = smem_u32(s_stage + (size_t)s * stage_bytes + A_BYTES);
+                        const uint8_t *blob = p.Wt + ((size_t)(k * n_cc + cc) * n_nt + nt) * (size_t)(ROWB * NT);
+                        if (p.diag & 1) {
+                            mbar_arrive(s_full + s);
+                        } else {
+                            mbar_arrive_expect_tx(s_full + s, (uint32_t)B_BYTES);
+                            bulk_g2s(b_base, blob, (uint32_t)B_BYTES, s_full + s);
+                        }
+                    }
+                }
+                mbar_arrive(s_tab_empty + b);
+            }
+        }
+    } else if (warp == 4) {
+        // ============================ MMA issuer ============================
+        const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, NT) : make_idesc_tf32(TILE_M, NT);
+        uint32_t g = 0;
+        int i = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, i++) {
+            const int b = i & 1, a = i & 1;
+            const long long tw0 = DBG_T();
+            mbar_wait(s_tab_full + b, (uint32_t)(i >> 1) & 1u);
+            const uint32_t *km = reinterpret_cast<const uint32_t *>(s_tabs + b * TL.bytes + TL.kmask);
+            const int n_items = __popc(km[0] | km[1]) * n_cc;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tab_empty + b);  // only the item count is needed from the table buffer
+            if (i >= 2) mbar_wait(s_acc_empty + a, (uint32_t)((i >> 1) - 1) & 1u);  // the epilogue drained this accumulator
+            tc_fence_after();
+            if (dbg && lane == 0) dbg[7] += clock64() - tw0;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * NT);
+            for (int it = 0; it < n_items; it++, g++) {
+                const int s = (int)(g % (uint32_t)S);
+                const uint32_t ph = (g / (uint32_t)S) & 1u;
+                const long long tm0 = DBG_T();
+                mbar_wait(s_full + s, ph);
+                const long long tm1 = DBG_T();
+                tc_fence_after();
+                proxy_fence_async();
+                const long long tm2 = DBG_T();
+                {
+                    const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
+                    const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < ROWB / 32; kk++) {  // one MMA consumes 32 bytes of K: 8 tf32 or 16 bf16
+                        const uint64_t ad = make_smem_desc(a_base + kk * 2 * A_LBO, A_LBO, 128);
+                        const uint64_t bd = make_smem_desc(b_base + kk * 2 * B_LBO, B_LBO, 128);
+                        umma_elect<BF16>(d_tmem, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    const long long tm3 = DBG_T();
+                    umma_commit_elect(s_empty + s);
+                    if (dbg && lane == 0) { dbg[2] += 1; dbg[3] += tm1 - tm0; dbg[4] += tm2 - tm1; dbg[5] += tm3 - tm2; dbg[6] += clock64() - tm3; }
+                }
+            }
+            if (lane == 0) s_acc_items[a] = n_items;
+            __syncwarp();
+            if (n_items > 0) umma_commit_elect(s_acc_full + a);
+            else if (lane == 0) mbar_arrive(s_acc_full + a);
+            __syncwarp();
+        }
+    } else {
+        // ============================ epilogue warps 0-3 ============================
+        // TMEM -> registers (lane = row) -> this warp's staging tile (XOR-swizzled 16-byte chunks) -> coalesced global
+        // stores (8 lanes write the 128 contiguous bytes of one row); the fused BatchNorm column sums come from the same
+        // staging tile.
+        uint8_t *stg = s_stg + warp * 4096;
+        const uint32_t stg_u32 = smem_u32(stg);
+        const int rsub = lane >> 3, cj = lane & 7;
+        int i = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, i++) {
+            const int a = i & 1;
+            const int64_t rt = w / n_nt;
+            const int nt = (int)(w % n_nt);
+            const int64_t trow = rt * TILE_M + warp * 32 + lane;
+            int64_t row = trow;
+            if (p.perm) row = __ldg(p.perm + trow);
+            const int my_dst = (row >= 0 && row < p.n_dst && !(p.diag & 16)) ? (int)row : -1;
+            const long long te0 = DBG_T();
+            mbar_wait(s_acc_full + a, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const long long te1 = DBG_T();
+            const int n_items = s_acc_items[a];
+            float *ts = p.tile_stats ? p.tile_stats + ((size_t)rt * 4 + warp) * 2 * p.Cd + nt * NT : nullptr;
+            if (n_items > 0) {
+                const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NT);
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    const int ncol = min(32, NT - c0);
+                    float4 ya[YADD ? 8 : 1];
+                    if (YADD) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int dst = __shfl_sync(0xFFFFFFFFu, my_dst, 4 * u + rsub);
+                            ya[u] = (dst >= 0 && cj * 4 < ncol) ? __ldg(reinterpret_cast<const float4 *>(p.Yadd + (int64_t)dst * p.Cd + nt * NT + c0 + cj * 4))
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    uint32_t v[32];
+                    {
+                        uint32_t lo[16], hi[16];
+                        tmem_ld16(t_row + (uint32_t)c0, lo);
+                        if (ncol == 32) tmem_ld16(t_row + (uint32_t)c0 + 16, hi);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { v[j] = lo[j]; v[16 + j] = ncol == 32 ? hi[j] : 0u; }
+                    }
+                    if (c0 + 32 >= NT) {  // last read of this accumulator: hand it back before the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s_acc_empty + a);
+                    }
+                    __syncwarp();  // the previous chunk's readers are done with the staging tile
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u32 + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                                     "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                                     : "memory");
+                    __syncwarp();
+                    if (ts && ncol == 32) {
+                        float sum = 0.f, sq = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < 32; r++) {
+                            const float x = *reinterpret_cast<const float *>(stg + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                            sum += x;
+                            sq = fmaf(x, x, sq);
+                        }
+                        ts[c0 + lane] = sum;
+                        ts[p.Cd + c0 + lane] = sq;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int r = 4 * u + rsub;
+                        const int dst = __shfl_sync(0xFFFFFFFFu, my_dst, r);
+                        if (dst >= 0 && cj * 4 < ncol) {
+                            uint4 q;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                                         : "r"(stg_u32 + r * 128 + ((cj ^ (r & 7)) << 4)));
+                            const int64_t o = (int64_t)dst * p.Cd + nt * NT + c0 + cj * 4;
+                            if (YADD) {
+                                q.x = __float_as_uint(__uint_as_float(q.x) + ya[u].x);
+                                q.y = __float_as_uint(__uint_as_float(q.y) + ya[u].y);
+                                q.z = __float_as_uint(__uint_as_float(q.z) + ya[u].z);
+                                q.w = __float_as_uint(__uint_as_float(q.w) + ya[u].w);
+                            }
+                            *reinterpret_cast<uint4 *>(p.Y + o) = q;
+                        }
+                    }
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_acc_empty + a);
+                if (my_dst >= 0) {
+                    float *yrow = p.Y + (int64_t)my_dst * p.Cd + nt * NT;
+                    const float *arow = YADD ? p.Yadd + (int64_t)my_dst * p.Cd + nt * NT : nullptr;
+                    for (int c0 = 0; c0 < NT; c0 += 4)
+                        *reinterpret_cast<float4 *>(yrow + c0) = arow ? __ldg(reinterpret_cast<const float4 *>(arow + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (ts)
+                    for (int c = lane; c < NT; c += 32) { ts[c] = 0.f; ts[p.Cd + c] = 0.f; }
+            }
+            if (dbg && tid == 0) { dbg[14] += te1 - te0; dbg[15] += clock64() - te1; }
+        }
+    }
+#undef DBG_T
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (dbg && tid == 0) dbg[1] = clock64();
 }
 
 template <bool WT>
@@ -659,6 +1106,9 @@ __global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const Wgr
             // A: units (input slice, channel atom, 32-row block) w, w+4, ...
             for (int u = pw; u < TM * G::A_ATOMS * G::RB; u += npw) {
                 const int a_atom = u / G::RB, a_rb = u % G::RB;  // a_atom counts atoms across the TM slices
+                // an atom entirely beyond Cs (Cs = 64 or 192: half of a 128-channel slice) is not fetched at all: its
+                // shared memory stays stale, which only reaches accumulator rows >= Cs, and those are never stored
+                if (m0 + a_atom * G::CPA >= p.Cs) continue;
                 const int a_ch = m0 + a_atom * G::CPA + cc * (16 / G::ES);
                 const bool a_ch_ok = a_ch < p.Cs;
 #pragma unroll
@@ -727,7 +1177,7 @@ __global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const Wgr
             }
             tc_fence_after();
             proxy_fence_async();
-            if (lane == 0) {
+            {   // all 32 lanes, converged (see umma_elect)
                 const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t b_base = a_base + A_BYTES;
                 for (int tm = 0; tm < TM; tm++) {
@@ -736,13 +1186,12 @@ __global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const Wgr
                     for (int g = 0; g < 4; g++) {
                         const uint64_t ad = make_smem_desc(a_base + tm * G::A_BYTES + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
                         const uint64_t bd = make_smem_desc(b_base + g * G::MMA_ADV, G::ATOM, G::SBO) | (G::LAYOUT << 61);
-                        umma<BF16>(tmem_base + (uint32_t)(tm * NT), ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                        umma_elect<BF16>(tmem_base + (uint32_t)(tm * NT), ad, bd, idesc, (it > 0 || g > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(s_empty + s);
-                if (it == n_items - 1) umma_commit(s_accum);
+                umma_commit_elect(s_empty + s);
+                if (it == n_items - 1) umma_commit_elect(s_accum);
             }
-            __syncwarp();
         }
         if (dbg && lane == 0) dbg[9] = dbg_wait_full;
     }
@@ -852,7 +1301,7 @@ static int launch_fwd_v1(const FwdParams &p, dim3 grid, size_t smem, cudaStream_
 static void conv_dbg_report(const char *tag, const long long *d_dbg, size_t n_cta) {
     long long *h = (long long *)malloc(n_cta * 16 * sizeof(long long));
     if (cudaMemcpy(h, d_dbg, n_cta * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) { free(h); return; }
-    double items = 0, main = 0, epi = 0, wait_e = 0, wait_f = 0, setup = 0;
+    double items = 0, main = 0, epi = 0, wait_e = 0, wait_f = 0, setup = 0, ph[6] = {0, 0, 0, 0, 0, 0};
     size_t live = 0;
     for (size_t i = 0; i < n_cta; i++) {
         const long long *d = h + i * 16;
@@ -864,6 +1313,7 @@ static void conv_dbg_report(const char *tag, const long long *d_dbg, size_t n_ct
         epi += (double)(d[4] - d[2]);
         wait_e += (double)d[8];
         wait_f += (double)d[9];
+        for (int j = 0; j < 6; j++) ph[j] += (double)d[10 + j];
     }
     // co-residency actually reached: CTAs of one SM share its clock64, so count overlapping lifetimes per SM
     int max_conc = 0;
@@ -890,6 +1340,10 @@ static void conv_dbg_report(const char *tag, const long long *d_dbg, size_t n_ct
                         "full %.0f) | setup %.0f  tail+epilogue %.0f cycles/cta | co-resident CTAs/SM max %d avg %.2f\n",
                 tag, live, items / live, main / items, wait_e / items, wait_f / items, setup / live, epi / live, max_conc,
                 busy > 0 ? area / busy : 0.0);
+    if (live && ph[0] + ph[1] + ph[2] > 0)
+        fprintf(stderr, "[conv dbg]   per item, producer thread 0: stale-zero+fence %.0f, LDGSTS issue %.0f, noinc arrive %.0f | MMA thread: fences "
+                        "%.0f, mma issue %.0f, commit %.0f\n", ph[0] / items, ph[1] / items, ph[2] / items, ph[3] / items, ph[4] / items,
+                ph[5] / items);
     free(h);
 }
 
@@ -954,6 +1408,73 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     p.tmem_cols = cols;
     const int chunks = ROWB / 16;
     const size_t stage_bytes = (size_t)chunks * A_LBO + (size_t)chunks * NT * 16;
+    // U2_CONV_KERNEL=ps selects the persistent warp-specialised kernel (measured slower than the co-resident-CTA kernel on
+    // every SPVCNN layer; read per call so that tests can exercise both)
+    const char *kern_env = getenv("U2_CONV_KERNEL");
+    const bool use_ps = (kern_env && !strcmp(kern_env, "ps")) || (getenv("U2_DEBUG_CONV_TIMING") && atoi(getenv("U2_DEBUG_CONV_TIMING")) == 2);
+    if (use_ps) {
+        // persistent warp-specialised kernel: one CTA per SM, the whole shared memory as one ring of stages
+        const PsTab TL = ps_tab_layout(K);
+        const size_t ps_fixed = 4 * 4096 + 2 * (size_t)TL.bytes + 1024;
+        int S = (int)((227 * 1024 - ps_fixed) / stage_bytes);
+        static const int s_cap = getenv("U2_CONV_PS_STAGES") ? atoi(getenv("U2_CONV_PS_STAGES")) : PS_MAX_STAGES;
+        if (S > s_cap) S = s_cap;
+        if (S > PS_MAX_STAGES) S = PS_MAX_STAGES;
+        U2_CHECK_ARG(S >= 2, "u2_conv_fwd_tc: tile does not fit shared memory");
+        p.stages = S;
+        int cols2 = 32;
+        while (cols2 < 2 * NT) cols2 <<= 1;
+        p.tmem_cols = cols2;
+        p.ld = perm ? ld : u2_ceil_div(n_dst, TILE_M) * TILE_M;  // rows walked by the tiles (the table is padded to ld >= this)
+        const size_t ps_smem = (size_t)S * stage_bytes + ps_fixed;
+        const int64_t n_work = (p.ld / TILE_M) * (Cd / NT);
+        static const int ps_ctas = getenv("U2_CONV_PS_CTAS") ? atoi(getenv("U2_CONV_PS_CTAS")) : U2_NUM_SMS;
+        dim3 pgrid((unsigned)(n_work < ps_ctas ? n_work : ps_ctas));
+        p.ld = ld;
+        p.n_tiles = perm ? ld / TILE_M : u2_ceil_div(n_dst, TILE_M);
+#define U2_PS_LAUNCH(RB, BF, YA)                                                                                                  \
+    do {                                                                                                                          \
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_ps_kernel<RB, BF, YA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem)); \
+        conv_fwd_ps_kernel<RB, BF, YA><<<pgrid, PS_THREADS, ps_smem, st>>>(p);                                                    \
+    } while (0)
+        static const int ps_dbg = getenv("U2_DEBUG_CONV_TIMING") && atoi(getenv("U2_DEBUG_CONV_TIMING")) == 2;
+        if (ps_dbg) {
+            U2_CUDA_OK(cudaMalloc(&p.dbg, (size_t)pgrid.x * 32 * sizeof(long long)));
+            U2_CUDA_OK(cudaMemsetAsync(p.dbg, 0, (size_t)pgrid.x * 32 * sizeof(long long), st));
+        }
+        if (bf16) {
+            if (ROWB == 128) { if (Yadd) U2_PS_LAUNCH(128, true, true); else U2_PS_LAUNCH(128, true, false); }
+            else { if (Yadd) U2_PS_LAUNCH(64, true, true); else U2_PS_LAUNCH(64, true, false); }
+        } else {
+            if (ROWB == 128) { if (Yadd) U2_PS_LAUNCH(128, false, true); else U2_PS_LAUNCH(128, false, false); }
+            else { if (Yadd) U2_PS_LAUNCH(64, false, true); else U2_PS_LAUNCH(64, false, false); }
+        }
+#undef U2_PS_LAUNCH
+        U2_LAUNCH_OK();
+        if (ps_dbg) {
+            U2_CUDA_OK(cudaStreamSynchronize(st));
+            const size_t nc = pgrid.x;
+            long long *h = (long long *)malloc(nc * 32 * sizeof(long long));
+            U2_CUDA_OK(cudaMemcpy(h, p.dbg, nc * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+            double a[32] = {0};
+            for (size_t c = 0; c < nc; c++) {
+                for (int j = 2; j < 32; j++) a[j] += (double)h[c * 32 + j];
+                a[0] += (double)(h[c * 32 + 1] - h[c * 32]);
+            }
+            const double it = a[2] > 0 ? a[2] : 1, pit = a[8] > 0 ? a[8] : 1, tl = a[18] > 0 ? a[18] : 1;
+            fprintf(stderr, "[conv ps dbg] Cs=%d Cd=%d NT=%d rows=%lld stages=%d ctas=%zu | cta cycles %.0f, tiles/cta %.1f, items/cta %.1f (%.0f cycles/item)\n"
+                            "[conv ps dbg]   MMA thread per item: wait full %.0f, fences %.0f, issue %.0f, commit %.0f | per tile: wait table/acc %.0f\n"
+                            "[conv ps dbg]   producer warp 0 per own item: wait empty %.0f, zero+fence %.0f, gather issue %.0f, arrive %.0f | per tile: wait table %.0f\n"
+                            "[conv ps dbg]   epilogue warp 0 per tile: wait acc %.0f, work %.0f | table warp 0 per tile: wait %.0f, work %.0f\n",
+                    Cs, Cd, NT, (long long)n_dst, S, nc, a[0] / nc, tl / nc, it / nc, a[0] / it,
+                    a[3] / it, a[4] / it, a[5] / it, a[6] / it, a[7] / tl,
+                    a[9] / pit, a[10] / pit, a[11] / pit, a[12] / pit, a[13] / tl,
+                    a[14] / tl, a[15] / tl, a[16] / tl, a[17] / tl);
+            free(h);
+            cudaFree(p.dbg);
+        }
+        return 0;
+    }
     // neighbour table + per-offset compact row lists / presence masks / counts + per-stage dirty masks + barriers
     const size_t fixed = (size_t)K * TILE_M * sizeof(int) + (size_t)K * (TILE_M + 16 + 4) + MAX_STAGES * 16 +
                          (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;

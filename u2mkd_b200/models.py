@@ -50,6 +50,9 @@ def build_family(ts) -> SimpleNamespace:
         feats = spf.spvoxelize(z.F, idx_query, counts)
         x = SparseTensor(feats, coords, 1)
         x.cmaps.setdefault(x.stride, x.coords)
+        prebuild = getattr(spf, "prebuild_maps", None)
+        if prebuild is not None and coords.is_cuda:
+            prebuild(x)  # product path: the kernel maps of every layer now, all host synchronisations before the first conv
         z.additional_features["idx_query"][1] = idx_query
         z.additional_features["counts"][1] = counts
         z.C = new_float_coord

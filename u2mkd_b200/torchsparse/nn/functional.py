@@ -12,7 +12,9 @@ from ..utils import make_ntuple
 from .utils import get_kernel_offsets, kernel_offsets_host
 
 __all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "spdownsample",
-           "conv3d", "unique_voxelize", "coord_query"]
+           "conv3d", "unique_voxelize", "coord_query", "build_map_for", "prebuild_maps"]
+
+prebuild_maps = ops.prebuild_maps
 
 
 def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1) -> torch.Tensor:
@@ -32,6 +34,27 @@ def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1)
     keep = torch.all((xyz % ss == 0) & (xyz >= cmin), dim=1)
     cand = torch.cat([xyz, b], dim=1)[keep].contiguous()
     return ops.downsample_coords(cand, (1, 1, 1))
+
+
+def build_map_for(cmaps: dict, kmaps: dict, key, in_coords=None):
+    """Kernel map `key` = (tensor_stride, kernel_size, stride, dilation) over the coordinate sets in `cmaps`: output
+    coordinates by spdownsample for a strided conv (registered under the output stride unless that set already exists),
+    then the neighbour tables.  Shared by F.conv3d (cache miss) and ops.prebuild_maps (start of the forward pass)."""
+    in_stride, kernel_size, stride, dilation = key
+    coords_in = cmaps[in_stride] if in_coords is None else in_coords
+    offsets = get_kernel_offsets(kernel_size, stride=in_stride, device=coords_in.device)
+    coords_out = coords_in
+    if any(s > 1 for s in stride):
+        out_stride = tuple(in_stride[a] * stride[a] for a in range(3))
+        coords_out = cmaps.get(out_stride)
+        if coords_out is None:
+            coords_out = spdownsample(coords_in, stride, kernel_size, in_stride)
+            cmaps[out_stride] = coords_out
+    kmap = ops.build_kernel_map(coords_in, coords_out, offsets, kernel_offsets_host(kernel_size, in_stride))
+    kmap.plan_key = key
+    ops._plan_note(key)
+    kmaps[key] = kmap
+    return kmap
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, stride=1, dilation=1,
@@ -68,12 +91,9 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size, bias=None, st
         key = (input.stride, kernel_size, stride, dilation)
         kmap = input.kmaps.get(key)
         if kmap is None:
-            offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=feats.device)
-            if any(s > 1 for s in stride):
-                coords = spdownsample(coords, stride, kernel_size, input.stride)
-            kmap = ops.build_kernel_map(input.coords, coords, offsets, kernel_offsets_host(kernel_size, input.stride))
-            input.kmaps[key] = kmap
-        elif any(s > 1 for s in stride):
+            input.cmaps.setdefault(input.stride, input.coords)
+            kmap = build_map_for(input.cmaps, input.kmaps, key, in_coords=input.coords)
+        if any(s > 1 for s in stride):
             coords = input.cmaps[out_stride]  # upstream skips this on a cache hit
         if epilogue is not None and bias is None:
             res = ops.sparse_conv_bn_relu(feats, weight, kmap, False, *epilogue, residual=residual, want_alias=want_alias)
