@@ -229,6 +229,13 @@ int u2_bn_bwd_apply_dual(const float *dy, const float *x, int64_t n, int32_t C, 
 /* fp32 -> bf16 (round to nearest even), n % 8 == 0: operand conversion for U2_MATH_BF16 */
 int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stream);
 
+/* Operand split of the "bf16x3" conv mode (fp32-grade results on the bf16 tensor-core kernels; the reference arithmetic is
+ * fp32, [TS backend/convolution/convolution_cuda.cu] at::mm): x fp32 [n, C] -> hi = bf16(x), lo = bf16(x - hi).
+ * out3 bf16 [n, 3C] = [hi | lo | hi] (rows for u2_conv_fwd* against weights stacked as [Whi; Whi; Wlo], i.e. the three
+ * significant terms of (hi + lo)(Whi + Wlo)), hi / lo bf16 [n, C] contiguous (u2_conv_wgrad_pairs operands); any of the
+ * three outputs may be NULL.  C % 8 == 0.                                                                              */
+int u2_split_bf16x3(const float *x, int64_t n, int32_t C, void *out3, void *hi, void *lo, u2_stream_t stream);
+
 /* ---- coordinate table of one coordinate set, built once per tensor stride and shared by the kernel maps and the
  * point<->voxel index queries of that stride (replaces the per-call table inside [TS nn/functional/query.py]
  * sphashquery, call sites core/models/utils.py:50,93).  table: u2_hash_table_bytes(n) bytes.  u2_coord_table_query:

@@ -488,3 +488,53 @@ def test_linear_bn_relu_fused_matches_torch_modules(tc, n, cin, cout, relu):
     ref.eval()
     with torch.no_grad():
         assert rel_err(seq(x.cuda()), ref(x.double())) < 1e-4
+
+
+@pytest.mark.parametrize("n,cin,cout,ks,stride", [
+    (6000, 64, 64, 3, 1), (3000, 96, 64, 3, 1), (2000, 128, 256, 3, 1), (4000, 64, 128, 2, 2), (1500, 512, 512, 3, 1),
+    (3000, 192, 384, 3, 1), (129, 64, 64, 3, 1), (2500, 32, 32, 3, 1), (2000, 16, 16, 3, 1)])
+def test_conv3d_bf16x3_meets_the_fp32_bar(tc, oracle, n, cin, cout, ks, stride):
+    """'bf16x3' (operands split into bf16 hi + lo, three tensor-core products, fp32 accumulation) against the fp32 oracle at
+    north_star's fp32 bar, rel 1e-4 in the max norm: outputs, input gradients and weight gradients — the tcgen05 parity
+    mode.  (16 -> 16 has no bf16 tile shape and takes the FFMA kernels, also inside the bar.)"""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin + cout)
+    c = rand_coords(rng, n)
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32))
+    conv_o = oracle.Conv3d(cin, cout, ks, stride)
+    conv_g = gts.nn.Conv3d(cin, cout, ks, stride)
+    conv_g.load_state_dict(conv_o.state_dict())
+    conv_g.cuda()
+    fo = f.clone().requires_grad_(True)
+    yo = conv_o(oracle.SparseTensor(fo, c))
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    tc.set_math("bf16x3")
+    assert tc.bf16x3_supported(cin, cout, ks ** 3) == (cin % 32 == 0 and cout % 32 == 0)
+    fg = f.clone().cuda().requires_grad_(True)
+    yg = conv_g(gts.SparseTensor(fg, c.cuda()))
+    yg.F.backward(g.cuda())
+    tc.set_math("fp32")
+    for got, want, what in zip((yg.F.detach(), fg.grad, conv_g.kernel.grad), (yo.F, fo.grad, conv_o.kernel.grad), ("out", "dgrad", "wgrad")):
+        assert rel_err(got, want) < 1e-4, (what, rel_err(got, want))
+
+
+def test_spvcnn_bf16x3_logits_within_fp32_bar(tc, oracle):
+    """Whole SPVCNN (cr = 1.0: every conv but the stem on the split-operand tensor-core path) against the fp64 oracle:
+    logits within rel 1e-4."""
+    from u2mkd_b200 import models, scans
+    import u2mkd_b200.torchsparse as gts
+    coords, feats = scans.make_batch([2], "nusc", 1, 0.2)
+    torch.manual_seed(3)
+    net_o = models.build_family(oracle.as_torchsparse_modules()["torchsparse"]).SPVCNN(cr=1.0, pres=0.2, vres=0.2, num_classes=17)
+    net_g = models.product().SPVCNN(cr=1.0, pres=0.2, vres=0.2, num_classes=17)
+    net_g.load_state_dict(net_o.state_dict())
+    net_g.cuda()
+    net_o.double()
+    net_o.dropout = net_g.dropout = torch.nn.Identity()
+    yo = net_o({"lidar": oracle.SparseTensor(torch.from_numpy(feats).double(), torch.from_numpy(coords))})["x_vox"].detach()
+    tc.set_math("bf16x3")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yg = net_g({"lidar": gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())})["x_vox"].detach()
+    tc.set_math("fp32")
+    assert rel_err(yg, yo.float()) < 1e-4, rel_err(yg, yo.float())

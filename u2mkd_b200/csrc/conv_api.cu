@@ -17,6 +17,7 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
 int u2_conv_pretile_tc(const float *W, int32_t w_transposed, int32_t K, int32_t Cs, int32_t Cd, int32_t math, void *blob,
                        cudaStream_t st);
 int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
+int u2_split_bf16x3_impl(const float *x, int64_t n, int32_t C, void *out3, void *hi, void *lo, cudaStream_t st);
 int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
                      int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
                      cudaStream_t st);
@@ -176,6 +177,17 @@ extern "C" int u2_cast_bf16(const float *x, int64_t n, void *y, u2_stream_t stre
 #else
     (void)x; (void)n; (void)y; (void)stream;
     u2_set_error("u2_cast_bf16: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+extern "C" int u2_split_bf16x3(const float *x, int64_t n, int32_t C, void *out3, void *hi, void *lo, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    U2_CHECK_ARG(x && (out3 || hi || lo), "u2_split_bf16x3: null pointer");
+    return u2_split_bf16x3_impl(x, n, C, out3, hi, lo, (cudaStream_t)stream);
+#else
+    (void)x; (void)n; (void)C; (void)out3; (void)hi; (void)lo; (void)stream;
+    u2_set_error("u2_split_bf16x3: built without the tcgen05 path");
     return 1;
 #endif
 }

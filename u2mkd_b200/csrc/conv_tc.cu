@@ -15,6 +15,7 @@
 //   No gather buffer, no output read-modify-write, no atomics: every output row is written
 //   once; (tile, offset) pairs without neighbours are skipped.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1237,6 +1238,35 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4 *__restrict
     y[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
+// fp32 rows -> bf16 "hi" (round to nearest) and "lo" = bf16(x - hi): x = hi + lo to ~2^-17 relative.  Writes the
+// concatenated operand rows [hi | lo | hi] (3C wide, conv forward / dgrad of the bf16x3 mode) and, optionally, contiguous
+// hi / lo matrices (wgrad operands).  One thread per 8 channels.
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float4 *__restrict__ x, int64_t n, int C8, uint4 *__restrict__ out3,
+                                                           uint4 *__restrict__ hi, uint4 *__restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C8) return;
+    const int64_t row = i / C8;
+    const int c = (int)(i % C8);
+    const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        l[e] = v[e] - h[e];  // exact in fp32
+    }
+    const uint4 H = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    const uint4 L = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    if (out3) {
+        uint4 *o = out3 + row * 3 * C8 + c;
+        o[0] = H;
+        o[C8] = L;
+        o[2 * C8] = H;
+    }
+    if (hi) hi[i] = H;
+    if (lo) lo[i] = L;
+}
+
 int pick_nt(int Cd) {
     const int tiles = (Cd + 255) / 256;
     if (Cd % tiles) return 0;
@@ -1514,6 +1544,16 @@ int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int
     }
     if (bf16) return ROWB == 128 ? launch_fwd_v1<128, true>(p, grid, smem, st) : launch_fwd_v1<64, true>(p, grid, smem, st);
     return ROWB == 128 ? launch_fwd_v1<128, false>(p, grid, smem, st) : launch_fwd_v1<64, false>(p, grid, smem, st);
+}
+
+int u2_split_bf16x3_impl(const float *x, int64_t n, int32_t C, void *out3, void *hi, void *lo, cudaStream_t st) {
+    U2_CHECK_ARG(C > 0 && C % 8 == 0, "u2_split_bf16x3: C %% 8 == 0 required (C=%d)", C);
+    U2_CHECK_ARG((((uintptr_t)x | (uintptr_t)out3 | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "u2_split_bf16x3: 16-byte alignment required");
+    if (n == 0) return 0;
+    const int64_t total = n * (C / 8);
+    split_bf16x3_kernel<<<(unsigned)u2_ceil_div(total, 256), 256, 0, st>>>((const float4 *)x, n, C / 8, (uint4 *)out3, (uint4 *)hi, (uint4 *)lo);
+    U2_LAUNCH_OK();
+    return 0;
 }
 
 int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st) {

@@ -17,7 +17,8 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import MATH_BF16, MATH_FP32, MATH_TF32, check, lib
 
-_MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
+MATH_BF16X3 = 3  # host-level mode: fp32-grade results from three bf16 tensor-core products (ConvolutionX3Fn)
+_MATH_NAMES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16, "bf16x3": MATH_BF16X3}
 _state = {"math": MATH_FP32, "sort_tiles": True, "overlap_rows": 1 << 30}
 
 # instrumentation used by bench.py: number of kernels this library launched, and an optional
@@ -31,7 +32,8 @@ def _count(n: int = 1) -> None:
 
 
 def set_math(mode: str) -> None:
-    """Arithmetic of the conv GEMMs: 'fp32' (FFMA, parity mode), 'tf32' or 'bf16' (tcgen05)."""
+    """Arithmetic of the conv GEMMs: 'fp32' (FFMA, parity mode), 'tf32' or 'bf16' (tcgen05), or 'bf16x3' (tcgen05, fp32-grade:
+    operands split into bf16 hi + lo, three products accumulated in fp32 — rel ~1e-5, the tensor-core parity mode)."""
     m = _MATH_NAMES[mode]
     if m != MATH_FP32 and not lib().u2_has_tensor_core_path():
         raise RuntimeError("this build of libu2mkd_b200.so has no tcgen05 conv path")
@@ -574,11 +576,12 @@ def _timed(kind, kmap, n_dst, K, c_src, c_dst, launch):
     conv_timer.record(kind, kmap, n_dst, K, c_src, c_dst, e0, e1)
 
 
-def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math, side=None, blob=None, yadd=None):
+def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math, side=None, blob=None, yadd=None, algo_c_src=None):
     """One fused gather-GEMM launch.  `blob`: weights already re-tiled by u2_conv_pretile for this direction (then `w` is
     not read); `yadd`: fp32 [n_dst, c_dst] added in the epilogue (sorted-tile path only)."""
     K, ld = table.shape
     n_src, c_src = x.shape
+    c_rep = c_src if algo_c_src is None else algo_c_src  # channels the conv timer credits (bf16x3 rows are 3 x as wide)
     y = torch.empty((n_dst, c_dst), dtype=torch.float32, device=x.device)
     assert (x.dtype == torch.bfloat16) == (math == MATH_BF16), (x.dtype, math)
     if blob is not None:
@@ -589,11 +592,11 @@ def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math,
         wptr = w.data_ptr()
     if side is not None and _state["sort_tiles"] and lib().u2_conv_tc_shape_supported(c_src, c_dst, K, math):
         tabP, perm, tmask = kmap.sorted_tables(side)
-        _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd_perm(
+        _timed(kind, kmap, n_dst, K, c_rep, c_dst, lambda: check(lib().u2_conv_fwd_perm(
             x.data_ptr(), n_src, c_src, wptr, int(w_transposed), tabP.data_ptr(), perm.data_ptr(), _ptr(yadd), ld, n_dst, K,
             c_dst, y.data_ptr(), math, _ptr(scratch), sbytes, _st())))
         return y
-    _timed(kind, kmap, n_dst, K, c_src, c_dst, lambda: check(lib().u2_conv_fwd(
+    _timed(kind, kmap, n_dst, K, c_rep, c_dst, lambda: check(lib().u2_conv_fwd(
         x.data_ptr(), n_src, c_src, wptr, int(w_transposed), table.data_ptr(), ld, n_dst, K, c_dst, y.data_ptr(),
         math, _ptr(scratch), sbytes, _st())))
     return y if yadd is None else y.add_(yadd)
@@ -680,8 +683,92 @@ class ConvolutionFn(Function):
         return grad_feats, grad_weight, None, None, None
 
 
+def split_bf16x3(x: torch.Tensor, want3: bool = True, want_parts: bool = True):
+    """fp32 [n, C] -> ([hi | lo | hi] bf16 [n, 3C], hi bf16 [n, C], lo bf16 [n, C]) with x = hi + lo to ~2^-17."""
+    x = x.contiguous()
+    n, c = x.shape
+    out3 = torch.empty((n, 3 * c), dtype=torch.bfloat16, device=x.device) if want3 else None
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=x.device) if want_parts else None
+    lo = torch.empty((n, c), dtype=torch.bfloat16, device=x.device) if want_parts else None
+    check(lib().u2_split_bf16x3(x.data_ptr(), n, c, _ptr(out3), _ptr(hi), _ptr(lo), _st()))
+    _count()
+    return out3, hi, lo
+
+
+def _split_weight(w: torch.Tensor):
+    """(Whi, Wlo) as fp32 tensors holding bf16-representable values: the bf16 rounding inside the weight pre-tiling is then exact."""
+    whi = w.bfloat16().float()
+    wlo = (w - whi).bfloat16().float()
+    return whi, wlo
+
+
+def bf16x3_supported(cin: int, cout: int, K: int) -> bool:
+    l = lib()
+    return bool(cin % 8 == 0 and cout % 8 == 0
+                and l.u2_conv_tc_shape_supported(3 * cin, cout, K, MATH_BF16) and l.u2_conv_tc_shape_supported(3 * cout, cin, K, MATH_BF16)
+                and l.u2_conv_wgrad_pairs_supported(cin, cout, K, MATH_BF16))
+
+
+class ConvolutionX3Fn(Function):
+    """Sparse conv in the 'bf16x3' mode: every fp32 operand is split as hi + lo (two bf16 numbers, 16 significant bits) and
+    x.w ~ hi.Whi + lo.Whi + hi.Wlo (the lo.Wlo term is below 2^-16 relative) is computed by the SAME bf16 tcgen05 kernels as
+    one conv over 3 x the input channels — rows [hi | lo | hi] against weights [Whi; Whi; Wlo] — with fp32 accumulation in
+    TMEM.  Measured per-operator error vs the fp32 oracle ~1e-5 (bar 1e-4): the tensor-core parity mode, ~3 x the conv flops
+    of 'bf16' instead of the FFMA kernels' 13 x slowdown.  dgrad the same way on dy; wgrad = three pair-list launches
+    (xhi, dyhi), (xlo, dyhi), (xhi, dylo) summed."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool):
+        _need_cuda(feats, weight)
+        feats = feats.contiguous().float()
+        weight = weight.contiguous().float()
+        K, cin, cout = weight.shape
+        if not transposed:
+            table, n_dst = kmap.nbr, kmap.n_out
+        else:
+            table, n_dst = kmap.nbrT, kmap.n_in
+        x3, xhi, xlo = split_bf16x3(feats, True, ctx.needs_input_grad[1])
+        whi, wlo = _split_weight(weight)
+        w3 = torch.cat([whi, whi, wlo], dim=1)  # [K, 3 cin, cout]
+        out = _conv_gather_gemm("fwd", kmap, x3, w3, False, table, n_dst, cout, MATH_BF16, side=bool(transposed), algo_c_src=cin)
+        ctx.save_for_backward(xhi, xlo, whi, wlo)
+        ctx.misc = (kmap, transposed, feats.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        xhi, xlo, whi, wlo = ctx.saved_tensors
+        kmap, transposed, n_src = ctx.misc
+        K, cin, cout = whi.shape
+        g = grad_output.contiguous().float()
+        g3, ghi, glo = split_bf16x3(g, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        grad_feats = grad_weight = None
+        if ctx.needs_input_grad[0]:
+            bwd_table = kmap.nbr if transposed else kmap.nbrT
+            wd3 = torch.cat([whi, whi, wlo], dim=2)  # [K, cin, 3 cout], read transposed by the kernel: rows of 3 cout -> cin
+            grad_feats = _conv_gather_gemm("dgrad", kmap, g3, wd3, True, bwd_table, n_src, cin, MATH_BF16, side=not transposed,
+                                           algo_c_src=cout)
+        if ctx.needs_input_grad[1]:
+            flat = kmap.flat_pairs
+            parts = []
+            for j, (xa, gb) in enumerate(((xhi, ghi), (xlo, ghi), (xhi, glo))):
+                dw = torch.empty((K, cin, cout), dtype=torch.float32, device=g.device)
+                _timed("wgrad", kmap, g.shape[0], K, cin if j == 0 else 0, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                    xa.data_ptr(), cin, gb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
+                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), dw.data_ptr(), MATH_BF16, _st())))
+                parts.append(dw)
+            grad_weight = parts[1].add_(parts[2]).add_(parts[0])  # small terms first
+        return grad_feats, grad_weight, None, None
+
+
 def sparse_conv(feats, weight, kmap: KernelMap, transposed: bool = False, math: Optional[int] = None):
-    return ConvolutionFn.apply(feats, weight, kmap, transposed, _state["math"] if math is None else math)
+    math = _state["math"] if math is None else math
+    if math == MATH_BF16X3:
+        K, cin, cout = weight.shape
+        if feats.is_cuda and bf16x3_supported(cin, cout, K):
+            return ConvolutionX3Fn.apply(feats, weight, kmap, transposed)
+        math = MATH_FP32  # shapes the bf16 tiles cannot hold (the Cin = 4 stem conv): the FFMA kernels, fp32-exact
+    return ConvolutionFn.apply(feats, weight, kmap, transposed, math)
 
 
 # -------------------------------------------------------------------------------- SyncBatchNorm statistics exchange
