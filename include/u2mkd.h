@@ -264,6 +264,33 @@ int32_t u2_syncbn_max_world(void);
 int u2_syncbn_exchange(double *vals, int32_t len, const void *const *peer_bufs, int32_t world, int32_t rank, uint64_t seq,
                        u2_stream_t stream);
 
+/* ---- variable-length window attention of third_party/SparseTransformer (`sptr_cuda`), the
+ * SphereFormer blocks between the down stages (core/models/sphereformer/spherical_transformer.py:165-283).
+ * Points are sorted by window; window w owns rows win_off[w] .. win_off[w+1]-1 and pairs sq_off[w] + i * n_w + j.
+ *
+ * u2_window_pairs replaces sptr_cuda.precompute_all_cuda (src/sptr/precompute/precompute_cuda_kernel.cu:4-34, bound at
+ * sptr/functional.py:166): index0_offsets / index1_offsets int32 [N], index0 / index1 int32 [M].
+ *
+ * u2_window_attn_fwd / _bwd replace, as ONE kernel per direction, the chain
+ *   dot_prod_with_idx_all_forward_cuda | attention_step1_forward_cuda   (src/sptr/rpe/...cu:116-170, attention/...cu:4-27)
+ *   scatter_softmax_csr                                                  (sptr/utils.py:81-95, torch_scatter)
+ *   attention_step2_with_rel_pos_value_forward_cuda | attention_step2_forward_cuda
+ * and their backward kernels.  q (already scaled), k, v, out: fp32 [N, h, head_dim]; lse fp32 [N, h] (log-sum-exp of
+ * every query's scores, saved for the backward); rel_idx int32 [M, 3] and table_{q,k,v} fp32 [L, 3, h, head_dim]
+ * (contextual relative position encoding) or all four NULL (pe_type 'none').  head_dim 16 or 32, L <= 64.
+ * The backward zeroes and accumulates dtable_*; dq / dk / dv are written once per row.                              */
+int u2_window_attn_supported(int32_t head_dim, int32_t L);
+int u2_window_pairs(const int32_t *win_off, const int32_t *sq_off, int32_t n_windows, int32_t *index0_offsets,
+                    int32_t *index1_offsets, int32_t *index0, int32_t *index1, u2_stream_t stream);
+int u2_window_attn_fwd(const float *q, const float *k, const float *v, const int32_t *win_off, const int32_t *sq_off,
+                       int32_t n_windows, int32_t h, int32_t head_dim, const int32_t *rel_idx, const float *table_q,
+                       const float *table_k, const float *table_v, int32_t L, float *out, float *lse, u2_stream_t stream);
+int u2_window_attn_bwd(const float *q, const float *k, const float *v, const int32_t *win_off, const int32_t *sq_off,
+                       int32_t n_windows, int32_t h, int32_t head_dim, const int32_t *rel_idx, const float *table_q,
+                       const float *table_k, const float *table_v, int32_t L, const float *out, const float *lse,
+                       const float *dout, float *dq, float *dk, float *dv, float *dtable_q, float *dtable_k,
+                       float *dtable_v, u2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,162 @@
+"""GPU parity of the sptr replacement against oracle/sptr_oracle.py.  Shapes follow the reference's own
+operator tests (third_party/SparseTransformer/test/test_attention_op_step1.py:11-15, test_relative_pos_encoding_op_step1_all.py:
+10-18: N = 3500 points in n = 150 windows, h = 6 heads of 16, L = 31 table rows), plus windows longer than one shared-memory
+chunk, single-point windows and head_dim 32.  Norm: max|a-b| / max|b| per tensor; bar 1e-4 (fp32 operator vs fp64 oracle),
+index outputs bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sptr_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def make_case(seed, n_windows, max_len, h, d, L, dtype=torch.float64, long_windows=()):
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(1, max_len + 1, size=n_windows)
+    for i, ln in enumerate(long_windows):
+        counts[i] = ln
+    counts = torch.from_numpy(counts.astype(np.int64))
+    N, M = int(counts.sum()), int((counts ** 2).sum())
+    g = torch.Generator().manual_seed(seed)
+    q, k, v = (torch.randn(N, h, d, generator=g, dtype=dtype) for _ in range(3))
+    tabs = [torch.randn(L, 3, h, d, generator=g, dtype=dtype) * 0.3 for _ in range(3)]
+    rel = torch.from_numpy(rng.integers(0, L, size=(M, 3)).astype(np.int32))
+    return counts, q * d ** -0.5, k, v, tabs, rel
+
+
+def test_precompute_all_bit_exact(cuda_lib):
+    from u2mkd_b200 import sptr
+    counts = torch.tensor([3, 2, 6], dtype=torch.int32)           # the reference's known-answer case
+    got = sptr.precompute_all(11, 3, 6, counts.cuda())
+    want = so.precompute_all(11, 3, 6, counts)
+    for a, b in zip(got, want):
+        assert a.dtype == torch.int32 and torch.equal(a.cpu(), b)
+    rng = np.random.default_rng(3)
+    counts = torch.from_numpy(rng.integers(1, 70, size=150).astype(np.int32))
+    N = int(counts.sum())
+    got = sptr.precompute_all(N, 150, int(counts.max()), counts.cuda())
+    want = so.precompute_all_fast(counts)
+    for a, b in zip(got, want):
+        assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("h,d,L,rel,long_windows", [(6, 16, 31, True, ()), (6, 16, 31, False, ()), (4, 16, 9, True, (150, 65, 64, 1)),
+                                                    (2, 32, 5, True, (70,)), (3, 32, 0, False, (130,))])
+def test_fused_window_attention_fwd_bwd(cuda_lib, h, d, L, rel, long_windows):
+    """functional.window_attention (one kernel per direction) against the oracle chain dot_prod_with_idx_all ->
+    scatter_softmax_csr -> attention_step2_with_rel_pos_value in fp64: output and the gradients of q, k, v and the three
+    tables."""
+    from u2mkd_b200.sptr import functional as F
+    counts, q, k, v, tabs, relidx = make_case(h * 100 + d + L, 150 if not long_windows else 12, 40, h, d, max(L, 1), long_windows=long_windows)
+    leaves = [t.clone().requires_grad_(True) for t in (q, k, v)] + [t.clone().requires_grad_(True) for t in tabs]
+    args = (relidx, leaves[3], leaves[4], leaves[5]) if rel else ()
+    want = so.window_attention(leaves[0], leaves[1], leaves[2], counts, *args)
+    go = torch.randn(want.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    want.backward(go)
+    win_off, sq_off = F.window_offsets(counts.cuda())
+    gl = [t.detach().float().cuda().requires_grad_(True) for t in leaves]
+    gargs = (relidx.cuda(), gl[3], gl[4], gl[5]) if rel else ()
+    got = F.window_attention(gl[0], gl[1], gl[2], win_off, sq_off, counts.shape[0], *gargs)
+    got.backward(go.float().cuda())
+    assert rel_err(got, want) < 1e-4, rel_err(got, want)
+    names = ["dq", "dk", "dv", "dtable_q", "dtable_k", "dtable_v"]
+    for i in range(6 if rel else 3):
+        assert rel_err(gl[i].grad, leaves[i].grad) < 1e-4, (names[i], rel_err(gl[i].grad, leaves[i].grad))
+
+
+def test_step_operators_match_oracle(cuda_lib):
+    """The reference-signature step operators (composable by hand) against the oracle, shapes of the reference's tests."""
+    from u2mkd_b200 import sptr
+    counts, q, k, v, tabs, relidx = make_case(7, 150, 45, 6, 16, 31, dtype=torch.float32)
+    N = q.shape[0]
+    i0o, i1o, i0, i1 = so.precompute_all_fast(counts)
+    g = lambda t: t.cuda()
+    n_max = int(counts.max())
+    s1 = sptr.attention_step1(g(q), g(k), g(i0), g(i0o), g(i1), g(i1o), n_max)
+    assert rel_err(s1, so.attention_step1(q, k, i0, i1)) < 1e-5
+    sa = sptr.dot_prod_with_idx_all(g(q), g(i0), g(i0o), g(k), g(i1), g(i1o), g(tabs[0]), g(tabs[1]), g(relidx), n_max)
+    want_sa = so.dot_prod_with_idx_all(q, i0, k, i1, tabs[0], tabs[1], relidx)
+    assert rel_err(sa, want_sa) < 1e-5
+    p = sptr.scatter_softmax_csr(sa, g(i0o).long(), dim=0)
+    want_p = so.scatter_softmax_csr(want_sa, i0o)
+    assert rel_err(p, want_p) < 1e-5
+    o2 = sptr.attention_step2(p, g(v), g(i0), g(i0o), g(i1), g(i1o), n_max)
+    assert rel_err(o2, so.attention_step2(want_p, v, i0, i1, N)) < 1e-5
+    o3 = sptr.attention_step2_with_rel_pos_value(p, g(v), g(i0), g(i0o), n_max, g(i1), g(i1o), g(tabs[2]), g(relidx))
+    assert rel_err(o3, so.attention_step2_with_rel_pos_value(want_p, v, i0, i1, tabs[2], relidx, N)) < 1e-5
+
+
+@pytest.mark.parametrize("shift", [False, True])
+def test_sparse_self_attention_end_to_end(cuda_lib, shift):
+    """get_indices_params + sparse_self_attention (sptr/modules.py:11-62, contextual relative position encoding) on a point
+    cloud: the fused path against the oracle composition on the oracle's own window partition — the result is invariant to
+    the order of windows and of points inside a window."""
+    from u2mkd_b200 import sptr
+    rng = np.random.default_rng(11)
+    n, h, d = 4000, 4, 16
+    xyz = torch.from_numpy(rng.uniform(0, 12, size=(n, 3)).astype(np.float32))
+    batch = torch.from_numpy(np.sort(rng.integers(0, 2, size=n)))
+    window, quant = np.array([1.5, 1.5, 1.5], np.float32), np.array([0.25, 0.25, 0.25], np.float32)
+    qgl = int((window[0] + 1e-4) / quant[0])
+    L = 2 * qgl - 1
+    g = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn(n, h, d, generator=g) for _ in range(3))
+    tabs = [torch.randn(L, 3, h, d, generator=g) * 0.2 for _ in range(3)]
+    # oracle: same recipe as sparse_self_attention, fp64, on its own partition
+    i0, i0o, n_max, i1, i1o, sort_idx, counts = so.get_indices_params(xyz, batch, window, shift)
+    xs = xyz[sort_idx].double()
+    ws = torch.from_numpy(window).double()
+    xq = torch.div((xs - xs.min(0)[0] + (0.5 * ws if shift else 0.0)) % ws, torch.from_numpy(quant).double(), rounding_mode="floor")
+    relidx = (xq[i0] - xq[i1] + qgl - 1).int()
+    want_sorted = so.window_attention(q[sort_idx].double(), k[sort_idx].double(), v[sort_idx].double(), counts, relidx,
+                                      *(t.double() for t in tabs))
+    want = torch.empty_like(want_sorted)
+    want[sort_idx] = want_sorted
+    # product
+    gi0, gi0o, gn_max, gi1, gi1o, gsort = sptr.get_indices_params(xyz.cuda(), batch.cuda(), window, shift)
+    assert gn_max == n_max and int(gi0o[-1]) == int(i0o[-1]) and getattr(gi0o, "_u2_windows", None) is not None
+    got = sptr.sparse_self_attention(q.cuda(), k.cuda(), v.cuda(), xyz.cuda(), gi0.int(), gi0o.int(), gn_max, gi1.int(), gi1o.int(),
+                                     gsort, window, shift, pe_type="contextual", rel_query=True, rel_key=True, rel_value=True,
+                                     quant_size=quant, quant_grid_length=qgl, relative_pos_query_table=tabs[0].cuda(),
+                                     relative_pos_key_table=tabs[1].cuda(), relative_pos_value_table=tabs[2].cuda())
+    assert rel_err(got, want) < 1e-4, rel_err(got, want)
+    # and the unfused fallback (offsets without the window boundaries) gives the same
+    plain = gi0o.int().clone()
+    got2 = sptr.sparse_self_attention(q.cuda(), k.cuda(), v.cuda(), xyz.cuda(), gi0.int(), plain, gn_max, gi1.int(), gi1o.int(),
+                                      gsort, window, shift, pe_type="contextual", rel_query=True, rel_key=True, rel_value=True,
+                                      quant_size=quant, quant_grid_length=qgl, relative_pos_query_table=tabs[0].cuda(),
+                                      relative_pos_key_table=tabs[1].cuda(), relative_pos_value_table=tabs[2].cuda())
+    assert rel_err(got2, want) < 1e-4
+
+
+def test_var_length_multihead_sa_module_trains(cuda_lib):
+    """VarLengthMultiheadSA (sptr/modules.py:65-200) forward + backward: every parameter gets a finite gradient, and the
+    cached window indices are reused by a second layer with the same indice_key."""
+    import u2mkd_b200
+    u2mkd_b200.install_as_sptr()
+    import sptr as sptr_mod
+    rng = np.random.default_rng(2)
+    n, C = 3000, 64
+    xyz = torch.from_numpy(rng.uniform(0, 10, size=(n, 3)).astype(np.float32)).cuda()
+    idx = torch.cat([torch.from_numpy(np.sort(rng.integers(0, 2, size=n))).float().cuda()[:, None], xyz], 1)
+    torch.manual_seed(0)
+    layers = [sptr_mod.VarLengthMultiheadSA(C, 4, "k0", 1.2, shift_win=False, pe_type="contextual", rel_query=True, rel_key=True,
+                                            rel_value=True, quant_size=0.2).cuda() for _ in range(2)]
+    x = torch.randn(n, C, device="cuda", requires_grad=True)
+    t = sptr_mod.SparseTrTensor(x, idx, spatial_shape=None, batch_size=2)
+    y = layers[0](t)
+    y.indice_dict = t.indice_dict
+    z = layers[1](y)
+    assert "k0" in t.indice_dict and z.query_feats.shape == (n, C)
+    z.query_feats.square().mean().backward()
+    for layer in layers:
+        for name, prm in layer.named_parameters():
+            assert prm.grad is not None and bool(torch.isfinite(prm.grad).all()) and float(prm.grad.abs().max()) > 0, name
+    assert bool(torch.isfinite(x.grad).all())

@@ -19,6 +19,16 @@ def install_as_torchsparse() -> None:
             sys.modules["torchsparse" + name[len(prefix):]] = mod
 
 
+def install_as_sptr() -> None:
+    """Register u2mkd_b200.sptr as `sptr` (third_party/SparseTransformer) in sys.modules: the SphereFormer blocks of
+    core/models/sphereformer/spherical_transformer.py then import it unchanged."""
+    pkg = importlib.import_module(__name__ + ".sptr")
+    prefix = pkg.__name__
+    for name, mod in list(sys.modules.items()):
+        if name == prefix or name.startswith(prefix + "."):
+            sys.modules["sptr" + name[len(prefix):]] = mod
+
+
 def set_math(mode: str) -> None:
     from . import ops
     ops.set_math(mode)
