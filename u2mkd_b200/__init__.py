@@ -29,6 +29,13 @@ def install_as_sptr() -> None:
             sys.modules["sptr" + name[len(prefix):]] = mod
 
 
+def install_reference_shims() -> list:
+    """timm.models.layers / torch_scatter / torchpack.utils.config stand-ins + the third_party.SparseTransformer.sptr import
+    path, for the reference's SphereFormer model files (u2mkd_b200/shims)."""
+    from .shims import install_reference_shims as _install
+    return _install()
+
+
 def set_math(mode: str) -> None:
     from . import ops
     ops.set_math(mode)
