@@ -130,6 +130,60 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(const float *__restr
     }
 }
 
+// ------------------------------------------------------------------ fwd, 4 input channels (the stem conv: x, y, z, intensity)
+// With Cs = 4 the generic kernel above spends 3/4 of its FMAs on padding (BK = 16) and two barriers per offset.  Here the
+// whole im2col row of a voxel — K offsets x 4 channels = 108 values for k = 3 — is gathered into shared memory once
+// (one 16-byte load per neighbour) next to the [K*4 x 64] weight slab, then one 64 x 64 x (K*4) register-tiled product:
+// same order of summation as the generic kernel (offsets ascending, channels ascending), so the results are bitwise equal.
+__global__ void __launch_bounds__(256) conv_fwd_c4_kernel(const float4 *__restrict__ X, const float *__restrict__ W,
+                                                          const int *__restrict__ table, int64_t ld, int64_t n_dst, int K, int Cd,
+                                                          float *__restrict__ Y) {
+    extern __shared__ __align__(16) float smem_c4[];
+    const int KC = K * 4;
+    float *As = smem_c4;                  // [KC][BM + 4]
+    float *Bs = smem_c4 + KC * (BM + 4);  // [KC][BN + 4]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    for (int e = tid; e < KC * (BN / 4); e += 256) {
+        const int kk = e / (BN / 4), n4 = (e % (BN / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + n4 + 3 < Cd) v = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)kk * Cd + n0 + n4));
+        *reinterpret_cast<float4 *>(&Bs[kk * (BN + 4) + n4]) = v;
+    }
+    for (int e = tid; e < K * BM; e += 256) {
+        const int r = e % BM, k = e / BM;
+        const int64_t row = row0 + r;
+        const int src = row < n_dst ? __ldg(table + (int64_t)k * ld + row) : -1;
+        const float4 v = src >= 0 ? __ldg(X + src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        As[(k * 4 + 0) * (BM + 4) + r] = v.x; As[(k * 4 + 1) * (BM + 4) + r] = v.y;
+        As[(k * 4 + 2) * (BM + 4) + r] = v.z; As[(k * 4 + 3) * (BM + 4) + r] = v.w;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int kk = 0; kk < KC; kk++) {
+        const float4 a = *reinterpret_cast<const float4 *>(&As[kk * (BM + 4) + ty * 4]);
+        const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk * (BN + 4) + tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t r = row0 + ty * 4 + i;
+        if (r >= n_dst) continue;
+        *reinterpret_cast<float4 *>(Y + r * Cd + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
 // ------------------------------------------------------------------ wgrad
 #define WG_ROWS 2048
 
@@ -242,6 +296,13 @@ int u2_conv_fwd_simt(const float *X, int64_t n_src, int32_t Cs, const float *W, 
     (void)n_src;
     if (n_dst == 0) return 0;
     dim3 grid((unsigned)u2_ceil_div(n_dst, BM), (unsigned)u2_ceil_div(Cd, BN));
+    if (!w_transposed && Cs == 4 && Cd % BN == 0 && K * 4 <= 128 && (((uintptr_t)X | (uintptr_t)W | (uintptr_t)Y) & 15) == 0) {
+        const size_t smem = (size_t)K * 4 * ((BM + 4) + (BN + 4)) * sizeof(float);
+        U2_CUDA_OK(cudaFuncSetAttribute(conv_fwd_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_c4_kernel<<<grid, 256, smem, st>>>((const float4 *)X, W, table, ld, n_dst, K, Cd, Y);
+        U2_LAUNCH_OK();
+        return 0;
+    }
     if (w_transposed)
         conv_fwd_simt_kernel<true><<<grid, 256, 0, st>>>(X, Cs, W, table, ld, n_dst, K, Cd, Y);
     else

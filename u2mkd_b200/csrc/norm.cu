@@ -126,17 +126,41 @@ __device__ __forceinline__ uint2 bf16x4(const float4 v) {
 // y = x * scale + shift (+ReLU); scale = invstd * gamma, shift = beta - mean * scale: computed once per thread
 template <bool RELU, int U>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float4 *__restrict__ x, int64_t n, int tx, int ty,
-                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                       const double *__restrict__ sums, float eps, float momentum,
+                                                       float *__restrict__ mean, float *__restrict__ invstd,
+                                                       float *__restrict__ running_mean, float *__restrict__ running_var,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
                                                        const float4 *__restrict__ res, float4 *__restrict__ y,
                                                        uint2 *__restrict__ yb) {
     const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
-    const int c = cx * 4;
+    const int c = cx * 4, C = tx * 4;
     float4 sc, sh;
     {
-        const float4 mu = ld4(mean + c), is = ld4(invstd + c), g = ld4(gamma + c), b = ld4(beta + c);
-        sc = make_float4(is.x * g.x, is.y * g.y, is.z * g.z, is.w * g.w);
-        sh = make_float4(b.x - mu.x * sc.x, b.y - mu.y * sc.y, b.z - mu.z * sc.z, b.w - mu.w * sc.w);
+        // mean / invstd of this thread's four channels straight from the (possibly all-reduced) fp64 sums — the arithmetic
+        // of bn_finalize_kernel, so no separate finalize launch; the first row of threads of CTA 0 also saves them for the
+        // backward and updates the running statistics
+        const double cnt = sums[2 * C] > 0.0 ? sums[2 * C] : 1.0;
+        float mu[4], is[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double m = sums[c + j] / cnt;
+            double var = sums[C + c + j] / cnt - m * m;
+            if (var < 0.0) var = 0.0;
+            mu[j] = (float)m;
+            is[j] = (float)(1.0 / sqrt(var + (double)eps));
+            if (blockIdx.x == 0 && ry == 0) {
+                mean[c + j] = mu[j];
+                invstd[c + j] = is[j];
+                if (running_mean) {
+                    const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+                    running_mean[c + j] = (1.f - momentum) * running_mean[c + j] + momentum * (float)m;
+                    running_var[c + j] = (1.f - momentum) * running_var[c + j] + momentum * (float)unbiased;
+                }
+            }
+        }
+        const float4 g = ld4(gamma + c), b = ld4(beta + c);
+        sc = make_float4(is[0] * g.x, is[1] * g.y, is[2] * g.z, is[3] * g.w);
+        sh = make_float4(b.x - mu[0] * sc.x, b.y - mu[1] * sc.y, b.z - mu[2] * sc.z, b.w - mu[3] * sc.w);
     }
     const int64_t step = (int64_t)gridDim.x * ty;
     auto put = [&](int64_t i, const float4 v) {
@@ -359,21 +383,23 @@ extern "C" int u2_bn_apply_dual(const float *x, int64_t n, int32_t C, const doub
     U2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)save_mean |
                    (uintptr_t)save_invstd | (uintptr_t)y_bf16 | (uintptr_t)residual) & 15) == 0,
                  "u2_bn_apply: pointers must be 16-byte aligned");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, eps, momentum, save_mean, save_invstd, running_mean,
-                                                         running_var);
-    U2_LAUNCH_OK();
-    if (n == 0) return 0;
+    if (n == 0) {  // nothing to normalise on this rank: only the statistics bookkeeping
+        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, eps, momentum, save_mean, save_invstd, running_mean,
+                                                             running_var);
+        U2_LAUNCH_OK();
+        return 0;
+    }
     const BnGeom g = bn_geom(C);
     static const int cap = bn_env("U2_BN_CAP_APPLY", 4), unroll = bn_env("U2_BN_U_APPLY", 2);
     const unsigned grid = bn_grid(n, g, cap);
     if (relu)
         BN_DISPATCH_U(unroll, (bn_apply_kernel<true, UU><<<grid, g.tx * g.ty, 0, st>>>(
-            (const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (const float4 *)residual, (float4 *)y,
-            (uint2 *)y_bf16)));
+            (const float4 *)x, n, g.tx, g.ty, sums, eps, momentum, save_mean, save_invstd, running_mean, running_var, gamma, beta,
+            (const float4 *)residual, (float4 *)y, (uint2 *)y_bf16)));
     else
         BN_DISPATCH_U(unroll, (bn_apply_kernel<false, UU><<<grid, g.tx * g.ty, 0, st>>>(
-            (const float4 *)x, n, g.tx, g.ty, save_mean, save_invstd, gamma, beta, (const float4 *)residual, (float4 *)y,
-            (uint2 *)y_bf16)));
+            (const float4 *)x, n, g.tx, g.ty, sums, eps, momentum, save_mean, save_invstd, running_mean, running_var, gamma, beta,
+            (const float4 *)residual, (float4 *)y, (uint2 *)y_bf16)));
     U2_LAUNCH_OK();
     return 0;
 }
