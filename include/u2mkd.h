@@ -291,6 +291,25 @@ int u2_window_attn_bwd(const float *q, const float *k, const float *v, const int
                        const float *dout, float *dq, float *dk, float *dv, float *dtable_q, float *dtable_k,
                        float *dtable_v, u2_stream_t stream);
 
+/* ---- point <-> pixel transforms of the student's fusion path (pure-torch loops in the reference, no
+ * native boundary there; these entries replace the bodies of
+ *   Point2Grid            core/models/fusion_blocks.py:217-238 and the per-scale body of
+ *                         core/models/nuscenes/spvcnn_swiftnet18_spformer_tsd_full.py:455-473
+ *                         (floor pixel, torch.unique(dim=0), scatter_add_, / count, sparse_coo_tensor().to_dense(), permute)
+ *   Feature_Gather + masked assignment   fusion_blocks.py:241-278, ...tsd_full.py:482-494 (grid_sample align_corners=True,
+ *                         zero padding; for a point seen by several cameras the LAST camera wins).
+ * feats fp32 [N, C] (C % 4 == 0), coord fp32 [V, N, 2] = (x, y) in [-1, 1], mask u8 [V, N], grids fp32 [V, C, H, W],
+ * counts int32 [V, H, W] (points per pixel; output of the forward, input of the backward).                              */
+size_t u2_point2grid_scratch_bytes(int32_t C, int32_t V, int32_t H, int32_t W);
+int u2_point2grid_fwd(const float *feats, const float *coord, const uint8_t *mask, int64_t N, int32_t C, int32_t V, int32_t H,
+                      int32_t W, float *grid, int32_t *counts, void *scratch, size_t scratch_bytes, u2_stream_t stream);
+int u2_point2grid_bwd(const float *dgrid, const float *coord, const uint8_t *mask, const int32_t *counts, int64_t N, int32_t C,
+                      int32_t V, int32_t H, int32_t W, float *dfeats, u2_stream_t stream);
+int u2_pixel_gather_fwd(const float *img, const float *coord, const uint8_t *mask, int64_t N, int32_t C, int32_t V, int32_t H,
+                        int32_t W, float *out, u2_stream_t stream);
+int u2_pixel_gather_bwd(const float *dout, const float *coord, const uint8_t *mask, int64_t N, int32_t C, int32_t V, int32_t H,
+                        int32_t W, float *dimg, u2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,74 @@ def get_indices_params(xyz, batch, window_size, shift_win):
     n_max = int(counts.max())
     i0o, i1o, i0, i1 = precompute_all_fast(counts)
     return i0.long(), i0o, n_max, i1.long(), i1o, sort_idx, counts
+
+
+# ------------------------------------------------------------------ module-level facade (what the SphereFormer blocks import)
+def to_3d_numpy(size):
+    """sptr/utils.py:9-19."""
+    import numbers
+    if isinstance(size, numbers.Number):
+        return np.array([size, size, size]).astype(np.float32)
+    if isinstance(size, list):
+        return np.array(size)
+    if isinstance(size, np.ndarray):
+        return size
+    raise ValueError("size is either a number, or a list, or a np.ndarray")
+
+
+class SparseTrTensor(object):
+    """sptr/__init__.py:4-33."""
+
+    def __init__(self, query_feats, query_indices, spatial_shape, batch_size, key_feats=None, value_feats=None, key_indices=None):
+        self.query_feats, self.key_feats, self.value_feats = query_feats, key_feats, value_feats
+        self.query_indices, self.key_indices = query_indices, key_indices
+        self.spatial_shape, self.batch_size = spatial_shape, batch_size
+        self.indice_dict = {}
+
+    def find_indice_params(self, key):
+        return None if key is None else self.indice_dict.get(key)
+
+
+def get_indices_params_ref(xyz, batch, window_size, shift_win):
+    """The reference's 6-tuple (sptr/utils.py:79)."""
+    i0, i0o, n_max, i1, i1o, sort_idx, _ = get_indices_params(xyz, batch, window_size, shift_win)
+    return i0, i0o, n_max, i1, i1o, sort_idx
+
+
+def sparse_self_attention(query, key, value, xyz, index_0, index_0_offsets, n_max, index_1, index_1_offsets, sort_idx,
+                          window_size, shift_win, pe_type='none', rel_query=False, rel_key=False, rel_value=False,
+                          quant_size=None, quant_grid_length=None, relative_pos_query_table=None,
+                          relative_pos_key_table=None, relative_pos_value_table=None, split_func=None):
+    """sptr/modules.py:11-62 line by line over the oracle operators (CPU, any float dtype)."""
+    query, key, value, xyz_ctg = query[sort_idx], key[sort_idx], value[sort_idx], xyz[sort_idx]
+    N = query.shape[0]
+    if pe_type == 'contextual' and rel_query and rel_key:
+        ws = torch.from_numpy(np.asarray(window_size)).to(xyz.dtype)
+        shift_size = 1 / 2 * ws if shift_win else 0.0
+        xyz_quant = (xyz_ctg - xyz_ctg.min(0)[0] + shift_size) % ws
+        xyz_quant = torch.div(xyz_quant, torch.from_numpy(np.asarray(quant_size)).to(xyz.dtype), rounding_mode='floor')
+        relative_position = xyz_quant[index_0.long()] - xyz_quant[index_1.long()]
+        relative_position_index = relative_position + quant_grid_length - 1
+        if split_func:
+            relative_position_index = split_func(xyz_ctg, index_0, index_1, relative_position_index.clone())
+            relative_position_index = torch.clamp(relative_position_index, 0, 2 * quant_grid_length - 1)
+        relative_position_index = relative_position_index.int()
+        attn_flat = dot_prod_with_idx_all(query, index_0, key, index_1, relative_pos_query_table, relative_pos_key_table,
+                                          relative_position_index)
+    else:
+        attn_flat = attention_step1(query, key, index_0, index_1)
+    softmax_attn_flat = scatter_softmax_csr(attn_flat, index_0_offsets)
+    if pe_type == 'contextual' and rel_value:
+        x = attention_step2_with_rel_pos_value(softmax_attn_flat, value, index_0, index_1, relative_pos_value_table,
+                                               relative_position_index, N)
+    else:
+        x = attention_step2(softmax_attn_flat, value, index_0, index_1, N)
+    out = torch.empty_like(x)
+    out[sort_idx] = x
+    return out
+
+
+def as_sptr_module():
+    from types import SimpleNamespace
+    return SimpleNamespace(to_3d_numpy=to_3d_numpy, SparseTrTensor=SparseTrTensor, sparse_self_attention=sparse_self_attention,
+                           get_indices_params=get_indices_params_ref)

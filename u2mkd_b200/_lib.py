@@ -105,6 +105,11 @@ _SIGNATURES = {
     "u2_bn_bwd_apply": (ctypes.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "u2_cast_bf16": (ctypes.c_int, [_p, _i64, _p, _p]),
     "u2_split_bf16x3": (ctypes.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
+    "u2_point2grid_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "u2_point2grid_fwd": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "u2_point2grid_bwd": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
+    "u2_pixel_gather_fwd": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
+    "u2_pixel_gather_bwd": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
     "u2_window_attn_supported": (ctypes.c_int, [_i32, _i32]),
     "u2_window_pairs": (ctypes.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p]),
     "u2_window_attn_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),

@@ -11,7 +11,7 @@
 //   4. sum the `world` vectors of the slot in rank order (bit-identical on every rank) in place of the input.
 // Exchanges of one group are totally ordered (every rank runs the same layers in the same order), so a slot is reused
 // only after every rank has published a LATER sequence number, i.e. after it finished reading: SLOTS = 4 is ample.
-// A rank that never arrives makes the others trap after a bounded spin instead of hanging the GPU.
+// A rank that never arrives makes the others trap after a bounded (~30 s) spin instead of hanging the GPU.
 #include <stdlib.h>
 
 #include "u2_common.cuh"
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) syncbn_exchange_kernel(double *__restrict
         const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(peers.p[rank]) + slot * SB_MAX_WORLD + tid;
         const long long t0 = clock64();
         while (ld_acquire_sys(flag) != seq) {
-            if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s: a rank left the lockstep
+            if (clock64() - t0 > 60000000000LL) __trap();  // ~30 s: a rank left the lockstep (start-up skew between ranks can reach seconds)
         }
     }
     __syncthreads();
