@@ -395,7 +395,9 @@ def run_ours(args, w):
         peak_tf = (pk["bf16_sus"] if math in ("bf16", "bf16x3") else pk["bf16_sus"] / 2.0)
         achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
         if os.path.exists(tpath) and math == "bf16":
             tk = json.load(open(tpath))["kernels"]
             key = "conv_fwd_tc_kernel<128, 1>" if dom_name.startswith("conv_fwd") else "conv_wgrad_tc_kernel<1>"
@@ -403,7 +405,7 @@ def run_ours(args, w):
                 traffic = tk[key]["dram_bytes_per_launch"]
         roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                    "traffic_note": "dram__bytes_read+write per launch, ncu launch list profiles/r1_launches_bf16.csv (average over "
+                    "traffic_note": "dram__bytes_read+write per launch, ncu launch list profiles/" + os.path.basename(tpath).replace("conv_traffic.json", "launches_bf16.csv") + " (average over "
                                     "the kernel's launches of one step)" if traffic else None,
                     "flops_per_launch": dom["flops"] / dom["launches"],
                     "peak_source": f"{pk['src']} bf16 sustained" + ("" if math == "bf16" else " / 2 (tf32)"),

@@ -196,12 +196,16 @@ def test_spvcnn_spformer_model_against_oracle(cuda_lib, oracle):
     q = torch.quantile(row_err, torch.tensor([0.5, 0.95, 0.999], dtype=torch.float64))
     bad = float((row_err > 1e-3).double().mean())
     print(f"rows {a.shape[0]}: row error median {q[0]:.2e}, p95 {q[1]:.2e}, p99.9 {q[2]:.2e}, max {row_err.max():.2e}, rows > 1e-3: {bad:.2%}")
-    assert q[0] < 2e-5 and q[1] < 2e-4 and bad < 0.02
+    assert q[0] < 2e-6 and q[1] < 2e-5 and bad < 0.02   # measured: median 9e-8, max 1.8e-6, no row beyond 1e-3
     worst = []
     for (name, pg), (_, po) in zip(net_g.named_parameters(), net_o.named_parameters()):
         assert pg.grad is not None and po.grad is not None, name
+        if name.startswith("point_transforms.") and name.endswith(".0.bias"):
+            continue  # Linear bias in front of a training-mode BatchNorm: zero gradient in exact arithmetic, rounding noise on both sides
         d = float((pg.grad.double().cpu() - po.grad.double()).norm() / po.grad.double().norm().clamp_min(1e-30))
         worst.append((d, name))
     worst.sort(reverse=True)
-    print("worst gradient tensors (relative L2):", [(f"{d:.1e}", n) for d, n in worst[:5]])
-    assert worst[0][0] < 5e-2 and np.median([d for d, _ in worst]) < 5e-3
+    print("worst gradient tensors (relative L2):", [(f"{d:.1e}", n) for d, n in worst[:12]])
+    # fp32 on both sides: the 49 BatchNorm layers make whole-model gradients of the fp32 CPU run itself noisy at the 2e-3 .. 9e-3
+    # level; measured worst 4.7e-3 (transformer_blocks.0.attn.proj.weight)
+    assert worst[0][0] < 2e-2 and np.median([d for d, _ in worst]) < 5e-3
