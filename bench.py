@@ -400,9 +400,11 @@ def run_ours(args, w):
             tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
         if os.path.exists(tpath) and math == "bf16":
             tk = json.load(open(tpath))["kernels"]
-            key = "conv_fwd_tc_kernel<128, 1>" if dom_name.startswith("conv_fwd") else "conv_wgrad_tc_kernel<1>"
-            if key in tk:
-                traffic = tk[key]["dram_bytes_per_launch"]
+            # every instantiation of the dominant kernel family (fwd: with / without the epilogue addend), launch-weighted
+            prefix = "conv_fwd_tc_kernel<128, 1" if dom_name.startswith("conv_fwd") else "conv_wgrad_tc_kernel<1"
+            hits = [v for k, v in tk.items() if k.startswith(prefix)]
+            if hits:
+                traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in hits) / sum(v["launches"] for v in hits)
         roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                     "traffic_note": "dram__bytes_read+write per launch, ncu launch list profiles/" + os.path.basename(tpath).replace("conv_traffic.json", "launches_bf16.csv") + " (average over "
