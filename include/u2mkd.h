@@ -150,6 +150,13 @@ int u2_conv_wgrad_pairs_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t mat
 int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb, int32_t Cd, const int32_t *nbr, int64_t ld,
                         int64_t n_rows, int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap,
                         float *dW, int32_t math, u2_stream_t stream);
+/* u2_conv_wgrad_pairs with a hint: offset dense_k (>= 0) pairs row j with row j for every j < n_rows (centre tap of a
+ * submanifold map; the single offset of a 1x1x1 conv / Linear layer) — those operand rows are contiguous and go through 2-D
+ * TMA tile loads instead of per-row gathers (bf16 mode).  dense_k = -1: identical to u2_conv_wgrad_pairs.  dense_ok: device
+ * int32 flag (NULL = trusted), 0 = the property does not hold for this map (duplicate coordinates): gather path.   */
+int u2_conv_wgrad_pairs_dense(const float *Xa, int32_t Cs, const float *dYb, int32_t Cd, const int32_t *nbr, int64_t ld,
+                              int64_t n_rows, int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap,
+                              float *dW, int32_t math, int32_t dense_k, const int32_t *dense_ok, u2_stream_t stream);
 
 /* ---- mask-sorted tile order for the tensor-core conv (no reference counterpart: the reference
  * walks offset-major pair lists; this is the output-stationary equivalent of that compaction).

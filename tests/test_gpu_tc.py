@@ -538,3 +538,56 @@ def test_spvcnn_bf16x3_logits_within_fp32_bar(tc, oracle):
     yg = net_g({"lidar": gts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda())})["x_vox"].detach()
     tc.set_math("fp32")
     assert rel_err(yg, yo.float()) < 1e-4, rel_err(yg, yo.float())
+
+
+@pytest.mark.parametrize("n,cin,cout,ks", [(30000, 64, 64, 3), (20000, 192, 192, 3), (9000, 256, 512, 3), (50000, 256, 192, 1), (300, 64, 128, 3)])
+def test_wgrad_dense_offset_tma_path_matches_gather_path(tc, monkeypatch, n, cin, cout, ks):
+    """The centre tap of a submanifold map (and the only offset of a 1x1x1 layer) pairs every row with itself: wgrad streams
+    those rows with 2-D TMA tile loads (u2_conv_wgrad_pairs_dense) instead of per-row gathers.  Same pairs, same order, same
+    MMA sequence: the weight gradient must agree with the gather path (U2_WGRAD_TMA=0) to the rounding of the fp32
+    reductions that combine the chunks."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(n + cin)
+    c = rand_coords(rng, n, extent=50).cuda()
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32)).cuda()
+    conv = gts.nn.Conv3d(cin, cout, ks).cuda()
+    tc.set_math("bf16")
+    grads = []
+    for tma in ("1", "0"):
+        monkeypatch.setenv("U2_WGRAD_TMA", tma)
+        conv.zero_grad()
+        x = gts.SparseTensor(f.clone(), c)
+        y = conv(x)
+        y.F.square().sum().backward()
+        grads.append(conv.kernel.grad.detach().clone())
+    monkeypatch.delenv("U2_WGRAD_TMA")
+    assert rel_err(grads[0], grads[1]) < 1e-5, rel_err(grads[0], grads[1])
+    if ks == 3:
+        km = list(x.kmaps.values())[0]
+        dk, flag = km.dense_hint()
+        assert dk == 13 and int(flag) == 1
+
+
+def test_wgrad_dense_hint_is_withdrawn_for_duplicate_coordinates(tc, oracle):
+    """A coordinate set with duplicates: the centre tap of a later duplicate points at the FIRST copy, not at itself, so the
+    device flag of dense_hint() is 0 and wgrad gathers; result against the fp32 oracle (bf16 bar)."""
+    import u2mkd_b200.torchsparse as gts
+    rng = np.random.default_rng(3)
+    c = rand_coords(rng, 3000)
+    c = torch.cat([c, c[:500]], 0)                      # 500 duplicates
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], 64)).astype(np.float32))
+    conv_o = oracle.Conv3d(64, 64, 3)
+    conv_g = gts.nn.Conv3d(64, 64, 3)
+    conv_g.load_state_dict(conv_o.state_dict())
+    conv_g.cuda()
+    yo = conv_o(oracle.SparseTensor(f.clone(), c))
+    g = torch.from_numpy(rng.standard_normal(yo.F.shape).astype(np.float32))
+    yo.F.backward(g)
+    tc.set_math("bf16")
+    x = gts.SparseTensor(f.clone().cuda(), c.cuda())
+    yg = conv_g(x)
+    yg.F.backward(g.cuda())
+    tc.set_math("fp32")
+    dk, flag = list(x.kmaps.values())[0].dense_hint()
+    assert dk == 13 and int(flag) == 0
+    assert rel_err(conv_g.kernel.grad, conv_o.kernel.grad) < 2e-2

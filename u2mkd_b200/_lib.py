@@ -118,6 +118,7 @@ _SIGNATURES = {
     "u2_kmap_pairs": (ctypes.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "u2_conv_wgrad_pairs_supported": (ctypes.c_int, [_i32, _i32, _i32, _i32]),
     "u2_conv_wgrad_pairs": (ctypes.c_int, [_p, _i32, _p, _i32, _p, _i64, _i64, _i32, _p, _p, _i32, _p, _i32, _p]),
+    "u2_conv_wgrad_pairs_dense": (ctypes.c_int, [_p, _i32, _p, _i32, _p, _i64, _i64, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p]),
 }
 
 EXPORTED = sorted(_SIGNATURES)

@@ -20,7 +20,7 @@ int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
 int u2_split_bf16x3_impl(const float *x, int64_t n, int32_t C, void *out3, void *hi, void *lo, cudaStream_t st);
 int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
                      int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
-                     cudaStream_t st);
+                     int32_t dense_k, const int32_t *dense_ok, cudaStream_t st);
 #endif
 
 extern "C" int u2_has_tensor_core_path(void) {
@@ -99,9 +99,26 @@ extern "C" int u2_conv_wgrad_pairs(const float *Xa, int32_t Cs, const float *dYb
 #ifdef U2_WITH_TC
     U2_CHECK_ARG(Xa && dYb && nbr && flat && nbsizes && dW, "u2_conv_wgrad_pairs: null pointer");
     U2_CHECK_ARG(u2_conv_wgrad_pairs_supported(Cs, Cd, K, math), "u2_conv_wgrad_pairs: unsupported shape/math");
-    return u2_conv_wgrad_tc(Xa, Cs, dYb, Cd, nbr, ld, n_rows, K, flat, nbsizes, swap, dW, math, (cudaStream_t)stream);
+    return u2_conv_wgrad_tc(Xa, Cs, dYb, Cd, nbr, ld, n_rows, K, flat, nbsizes, swap, dW, math, -1, nullptr, (cudaStream_t)stream);
 #else
     u2_set_error("u2_conv_wgrad_pairs: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+// Same, with a hint: offset `dense_k` (>= 0) of this map pairs row j with row j for EVERY j < n_rows — the centre tap of a
+// submanifold map, or the only offset of a 1x1x1 conv / Linear layer (identity map); both matrices then have n_rows rows.
+// Those pairs' operand rows are contiguous and are streamed with 2-D TMA tile loads instead of per-row gathers.
+// dense_ok (device int32, may be NULL = trusted): 0 makes the kernel take the gather path for that offset after all.
+extern "C" int u2_conv_wgrad_pairs_dense(const float *Xa, int32_t Cs, const float *dYb, int32_t Cd, const int32_t *nbr, int64_t ld,
+                                         int64_t n_rows, int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap,
+                                         float *dW, int32_t math, int32_t dense_k, const int32_t *dense_ok, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    U2_CHECK_ARG(Xa && dYb && nbr && flat && nbsizes && dW, "u2_conv_wgrad_pairs_dense: null pointer");
+    U2_CHECK_ARG(u2_conv_wgrad_pairs_supported(Cs, Cd, K, math), "u2_conv_wgrad_pairs_dense: unsupported shape/math");
+    return u2_conv_wgrad_tc(Xa, Cs, dYb, Cd, nbr, ld, n_rows, K, flat, nbsizes, swap, dW, math, dense_k, dense_ok, (cudaStream_t)stream);
+#else
+    u2_set_error("u2_conv_wgrad_pairs_dense: built without the tcgen05 path");
     return 1;
 #endif
 }

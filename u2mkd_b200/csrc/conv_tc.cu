@@ -1001,6 +1001,8 @@ struct WgradParams {
     float *dW;
     int64_t ld;
     int Cs, Cd, K, NT, stages, tmem_cols, swap, n_mt, n_nt, cp_mode, TM;
+    int dense_k;   // offset whose pairs are (row j, row j) for every row (centre tap of a submanifold map, k = 1 layers), or -1
+    const int *dense_ok;  // optional device flag: 0 = the map does not have that property after all (duplicate coordinates) -> gather path
     int wg_pairs;  // pairs per CTA, multiple of 128, <= WG_PAIRS
     long long *dbg;  // optional per-CTA phase clocks (U2_DEBUG_CONV_TIMING)
     int npw;         // producer warps: 4 (warps 0-3) or 8 (+ warps 6-9) when only one CTA fits an SM
@@ -1008,8 +1010,18 @@ struct WgradParams {
 
 constexpr int WG_MAX_THREADS = NUM_THREADS + 4 * 32;  // + 4 optional extra producer warps (warps 6-9)
 
+// 2-D tile load through the TMA engine: box {64 channels, 64 rows} of a row-major bf16 matrix, SWIZZLE_128B — the byte
+// pattern r * 128 + ((chunk ^ (r & 7)) << 4) that the gather producers write (WgGeom<true>::swz); rows past the end of the
+// matrix are zero-filled by the hardware.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int c0, int r0, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(r0)
+                 : "memory");
+}
+
 template <bool BF16>
-__global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tmapA,
+                                                                       const __grid_constant__ CUtensorMap tmapB) {
     using G = WgGeom<BF16>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int NT = p.NT;
@@ -1039,9 +1051,13 @@ __global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const Wgr
     long long *dbg = p.dbg ? p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
     if (dbg && tid == 0) { dbg[0] = clock64(); dbg[6] = n_items; }
 
+    // Offset `dense_k` of a submanifold / identity map pairs every row with itself (the centre tap; all of a 1x1x1 conv or
+    // Linear layer): its operand rows are CONTIGUOUS, so one thread streams them with 2-D TMA tile loads — 5-7 instructions
+    // per 64-pair stage instead of ~100 warp-level LDGSTS, and no pair-list prologue.  ~20 % of the pairs of a k = 3 map.
+    const bool dense = BF16 && k == p.dense_k && (p.dense_ok == nullptr || __ldg(p.dense_ok) != 0);
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) {
-            mbar_init(s_full + s, p.npw * 32);
+            mbar_init(s_full + s, dense ? 1 : p.npw * 32);
             mbar_init(s_empty + s, 1);
         }
         mbar_init(s_accum, 1);
@@ -1054,7 +1070,7 @@ __global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const Wgr
     // (a-row, b-row) of every pair of the chunk; padded to a whole stage with -1.  Two dependent global loads per
     // pair (flat index -> neighbour table): 8 pairs per thread are in flight at a time, otherwise this prologue is a
     // chain of ~2 x 11 exposed L2 latencies (measured 20 k cycles per CTA before batching).
-    {
+    if (!dense) {
         const int *flat = p.flat + koff + c0;
         const int padded = n_items * G::KR;
         const int nthr = blockDim.x;
@@ -1091,6 +1107,25 @@ __global__ void __launch_bounds__(WG_MAX_THREADS) conv_wgrad_tc_kernel(const Wgr
         const int cc = lane & 7;     // 16-byte chunk inside a 128-byte atom row
         const int rsub = lane >> 3;  // pair inside a group of 4
         const size_t a_pitch = (size_t)p.Cs * G::ES, b_pitch = (size_t)p.Cd * G::ES;
+        if (dense) {
+            if (tid == 0) {
+                int n_a = 0;  // channel atoms of the A side that exist (an atom beyond Cs is never fetched, see below)
+                for (int a = 0; a < TM * G::A_ATOMS; a++) n_a += (m0 + a * G::CPA < p.Cs) ? 1 : 0;
+                const uint32_t tx = (uint32_t)(n_a + n_batoms) * (uint32_t)G::ATOM;
+                for (int it = 0; it < n_items; it++) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(s_empty + s, ph ^ 1u);
+                    const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t b_base = a_base + A_BYTES;
+                    const int r0 = c0 + it * G::KR;  // pair j of the offset = (row j, row j)
+                    mbar_arrive_expect_tx(s_full + s, tx);
+                    for (int a = 0; a < TM * G::A_ATOMS; a++)
+                        if (m0 + a * G::CPA < p.Cs) tma_load_2d(a_base + a * G::ATOM, &tmapA, m0 + a * G::CPA, r0, s_full + s);
+                    for (int b = 0; b < n_batoms; b++) tma_load_2d(b_base + b * G::ATOM, &tmapB, n0 + b * G::CPA, r0, s_full + s);
+                }
+            }
+        } else
         for (int it = 0; it < n_items; it++) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -1564,10 +1599,33 @@ int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st) {
     return 0;
 }
 
-// X / dY: fp32 rows (math TF32) or bf16 rows (math BF16)
+typedef CUresult (*U2EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor map over a row-major bf16 matrix [rows, C]: box = 64 channels x 64 rows, SWIZZLE_128B, zero fill outside
+static bool u2_make_rows_tmap(CUtensorMap *tm, const void *base, int64_t rows, int C) {
+    static U2EncodeTiledFn encode = []() -> U2EncodeTiledFn {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (U2EncodeTiledFn)ptr;
+    }();
+    if (!encode || rows <= 0 || ((uintptr_t)base & 15) || (C * 2) % 16) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {64u, 64u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// X / dY: fp32 rows (math TF32) or bf16 rows (math BF16).  dense_k >= 0: offset dense_k pairs row j with row j for every
+// j < n_rows (both matrices have n_rows rows) — its operands are then streamed with TMA tile loads (bf16 only).
 int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, const int32_t *nbr, int64_t ld, int64_t n_rows,
                      int32_t K, const int32_t *flat, const int32_t *nbsizes, int32_t swap, float *dW, int32_t math,
-                     cudaStream_t st) {
+                     int32_t dense_k, const int32_t *dense_ok, cudaStream_t st) {
     const bool bf16 = math == U2_MATH_BF16;
     const int NT = pick_nt(Cd);
     U2_CHECK_ARG(NT && Cs % (bf16 ? 8 : 4) == 0 && K <= 32, "u2_conv_wgrad_tc: unsupported shape Cs=%d Cd=%d K=%d", Cs, Cd, K);
@@ -1640,16 +1698,24 @@ int u2_conv_wgrad_tc(const void *X, int32_t Cs, const void *dY, int32_t Cd, cons
         U2_CUDA_OK(cudaMalloc(&p.dbg, n_cta * 16 * sizeof(long long)));
         U2_CUDA_OK(cudaMemsetAsync(p.dbg, 0, n_cta * 16 * sizeof(long long), st));
     }
+    alignas(64) CUtensorMap tmA, tmB;
+    memset(&tmA, 0, sizeof tmA);
+    memset(&tmB, 0, sizeof tmB);
+    const int tma_on = getenv("U2_WGRAD_TMA") ? atoi(getenv("U2_WGRAD_TMA")) : 1;  // read per call: tests compare both paths
+    p.dense_k = -1;
+    if (bf16 && tma_on && dense_k >= 0 && dense_k < K && u2_make_rows_tmap(&tmA, X, n_rows, Cs) && u2_make_rows_tmap(&tmB, dY, n_rows, Cd))
+        p.dense_k = dense_k;
+    p.dense_ok = dense_ok;
     if (bf16) {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared));
-        conv_wgrad_tc_kernel<true><<<grid, threads, smem, st>>>(p);
+        conv_wgrad_tc_kernel<true><<<grid, threads, smem, st>>>(p, tmA, tmB);
     } else {
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         U2_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         getenv("U2_NO_CARVEOUT") ? -1 : (int)cudaSharedmemCarveoutMaxShared));
-        conv_wgrad_tc_kernel<false><<<grid, threads, smem, st>>>(p);
+        conv_wgrad_tc_kernel<false><<<grid, threads, smem, st>>>(p, tmA, tmB);
     }
     U2_LAUNCH_OK();
     if (debug_timing) {

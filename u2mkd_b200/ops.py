@@ -358,6 +358,7 @@ def prebuild_maps(x) -> int:
             kmap.sorted_tables(True)
         if "flat" in flags:
             kmap.flat_pairs
+            kmap.dense_hint()
     return built
 
 
@@ -421,6 +422,24 @@ class KernelMap:
                 _count(8)
             self._sorted[key] = (tabP, perm, tmask)
         return self._sorted[key]
+
+    def dense_hint(self):
+        """(dense_k, flag): offset of a submanifold / identity map that pairs every row with itself (the centre tap; the only
+        offset of a 1x1x1 layer) and a device int32 flag saying that it really does (a coordinate set with duplicates would
+        not) — the wgrad kernel streams that offset's rows with TMA tile loads.  (-1, None) for strided / transposed maps."""
+        if getattr(self, "_dense", None) is None:
+            k = -1
+            if self.same_coords and self.n_in == self.n_out and self.offsets_host is not None:
+                for i, o in enumerate(self.offsets_host):
+                    if all(v == 0 for v in o):
+                        k = i
+            flag = None
+            if k >= 0:
+                n = self.n_out
+                flag = (self.nbr[k, :n] == torch.arange(n, dtype=torch.int, device=self.nbr.device)).all().to(torch.int32).view(1)
+                _count(3)
+            self._dense = (k, flag)
+        return self._dense
 
     @property
     def flat_pairs(self) -> torch.Tensor:
@@ -514,6 +533,7 @@ def identity_kernel_map(n: int, device) -> KernelMap:
         km = KernelMap(nbr, nbr, nbsizes, n, n, [[0, 0, 0]], True)
         km._sorted = {False: (nbr, nbr[0], None), True: (nbr, nbr[0], None)}  # every row has the same mask: nothing to sort
         km._flat = nbr[0]                                                      # flat pair list k * ld + row = row
+        km._dense = (0, torch.ones(1, dtype=torch.int32, device=device))       # every pair is (row j, row j)
         _count(2)
         _identity_maps[key] = km
     return km
@@ -669,9 +689,11 @@ class ConvolutionFn(Function):
             if m_wgrad != MATH_FP32 and lib().u2_conv_wgrad_pairs_supported(cin, cout, K, m_wgrad):
                 flat = kmap.flat_pairs
                 gw = g_bf16 if m_wgrad == MATH_BF16 else g
-                _timed("wgrad", kmap, g.shape[0], K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                dk, dflag = kmap.dense_hint() if m_wgrad == MATH_BF16 else (-1, None)
+                _timed("wgrad", kmap, g.shape[0], K, cin, cout, lambda: check(lib().u2_conv_wgrad_pairs_dense(
                     x_op.data_ptr(), cin, gw.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
-                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), m_wgrad, _st())))
+                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), m_wgrad, dk, _ptr(dflag),
+                    _st())))
             else:
                 n_dst = g.shape[0]
                 m = MATH_FP32 if m_wgrad == MATH_BF16 else m_wgrad
@@ -751,11 +773,12 @@ class ConvolutionX3Fn(Function):
         if ctx.needs_input_grad[1]:
             flat = kmap.flat_pairs
             parts = []
+            dk, dflag = kmap.dense_hint()
             for j, (xa, gb) in enumerate(((xhi, ghi), (xlo, ghi), (xhi, glo))):
                 dw = torch.empty((K, cin, cout), dtype=torch.float32, device=g.device)
-                _timed("wgrad", kmap, g.shape[0], K, cin if j == 0 else 0, cout, lambda: check(lib().u2_conv_wgrad_pairs(
+                _timed("wgrad", kmap, g.shape[0], K, cin if j == 0 else 0, cout, lambda: check(lib().u2_conv_wgrad_pairs_dense(
                     xa.data_ptr(), cin, gb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
-                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), dw.data_ptr(), MATH_BF16, _st())))
+                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), dw.data_ptr(), MATH_BF16, dk, _ptr(dflag), _st())))
                 parts.append(dw)
             grad_weight = parts[1].add_(parts[2]).add_(parts[0])  # small terms first
         return grad_feats, grad_weight, None, None
@@ -1031,11 +1054,13 @@ class ConvBNReLUFn(Function):
         if ctx.needs_input_grad[2]:
             grad_weight = torch.empty_like(weight)
             flat = kmap.flat_pairs
+            dk, dflag = kmap.dense_hint()
 
             def wgrad():
-                _timed("wgrad" + tag, kmap, n, K, cin, cout, lambda: check(l.u2_conv_wgrad_pairs(
+                _timed("wgrad" + tag, kmap, n, K, cin, cout, lambda: check(l.u2_conv_wgrad_pairs_dense(
                     xb.data_ptr(), cin, dyb.data_ptr(), cout, kmap.nbr.data_ptr(), kmap.nbr.shape[1], kmap.n_out, K,
-                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, _st())))
+                    flat.data_ptr(), kmap.nbsizes.data_ptr(), int(transposed), grad_weight.data_ptr(), MATH_BF16, dk, _ptr(dflag),
+                    _st())))
 
             if side is not None:
                 side.wait_stream(torch.cuda.current_stream(dev))
