@@ -114,39 +114,69 @@ extern "C" int u2_voxelize_fwd(const float *feats, int64_t n_pts, int32_t C, con
 }
 
 // ------------------------------------------------------------------ voxelize bwd (pure gather)
-__global__ void __launch_bounds__(256) voxelize_bwd_kernel(const float *__restrict__ gout, int64_t n_vox, int C, int W,
+// gfeats[p, :] = gout[idx[p], :] / counts[idx[p]].  A thread owns U 16-byte pieces of one point's row (strided by the group): the
+// index / count chain (two dependent loads) is paid once per U pieces and the U row loads are in flight together — with one
+// piece per thread the kernel sat at 0.41-0.48 of the HBM peak, bound by that three-deep dependent chain per 16 bytes.
+template <int U>
+__global__ void __launch_bounds__(256) voxelize_bwd_vec_kernel(const float4 *__restrict__ gout, int64_t n_vox, int per_row,
+                                                               const int *__restrict__ idx, const int *__restrict__ counts,
+                                                               float4 *__restrict__ gfeats, int64_t n_pts) {
+    const int groups = per_row / U;  // thread groups per row
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pts * groups) return;
+    const int64_t p = t / groups;
+    const int v0 = (int)(t - p * groups);  // pieces v0, v0 + groups, ...: every load / store instruction of a warp stays contiguous
+    const int vox = __ldg(idx + p);
+    const bool ok = vox >= 0 && vox < n_vox;
+    const int cnt = ok ? __ldg(counts + vox) : 0;
+    float4 r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && cnt > 0) {
+        const float4 *src = gout + (int64_t)vox * per_row + v0;
+#pragma unroll
+        for (int u = 0; u < U; u++) r[u] = __ldg(src + u * groups);
+        const float c = (float)cnt;
+#pragma unroll
+        for (int u = 0; u < U; u++) { r[u].x /= c; r[u].y /= c; r[u].z /= c; r[u].w /= c; }
+    }
+    float4 *dst = gfeats + p * per_row + v0;
+#pragma unroll
+    for (int u = 0; u < U; u++) dst[u * groups] = r[u];
+}
+
+__global__ void __launch_bounds__(256) voxelize_bwd_kernel(const float *__restrict__ gout, int64_t n_vox, int C,
                                                            const int *__restrict__ idx, const int *__restrict__ counts,
                                                            float *__restrict__ gfeats, int64_t n_pts) {
-    // W = elements per thread (4 -> float4 path, 1 -> scalar)
-    const int per_row = C / W;
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_pts * per_row) return;
-    int64_t p = t / per_row;
-    int v = (int)(t - p * per_row);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // scalar path: C not a multiple of 4 / unaligned
+    if (t >= n_pts * C) return;
+    int64_t p = t / C;
+    int v = (int)(t - p * C);
     int vox = __ldg(idx + p);
     const bool ok = vox >= 0 && vox < n_vox;
     int cnt = ok ? __ldg(counts + vox) : 0;
-    if (W == 4) {
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && cnt > 0) {
-            r = __ldg(reinterpret_cast<const float4 *>(gout) + (int64_t)vox * per_row + v);
-            float c = (float)cnt;
-            r.x /= c; r.y /= c; r.z /= c; r.w /= c;
-        }
-        reinterpret_cast<float4 *>(gfeats)[t] = r;
-    } else {
-        gfeats[t] = (ok && cnt > 0) ? __ldg(gout + (int64_t)vox * C + v) / (float)cnt : 0.f;
-    }
+    gfeats[t] = (ok && cnt > 0) ? __ldg(gout + (int64_t)vox * C + v) / (float)cnt : 0.f;
 }
 
 extern "C" int u2_voxelize_bwd(const float *gout, int64_t n_vox, int32_t C, const int32_t *idx, const int32_t *counts,
                                float *gfeats, int64_t n_pts, u2_stream_t stream) {
     if (n_pts == 0) return 0;
     U2_CHECK_ARG(C > 0, "u2_voxelize_bwd: C=%d", C);
+    cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (C % 4 == 0) && (((uintptr_t)gout | (uintptr_t)gfeats) & 15) == 0;
-    const int W = vec ? 4 : 1;
-    voxelize_bwd_kernel<<<(unsigned)u2_ceil_div(n_pts * (C / W), 256), 256, 0, (cudaStream_t)stream>>>(
-        gout, n_vox, C, W, idx, counts, gfeats, n_pts);
+    if (vec) {
+        const int per_row = C / 4;
+        const float4 *g4 = (const float4 *)gout;
+        float4 *o4 = (float4 *)gfeats;
+        if (per_row % 4 == 0)
+            voxelize_bwd_vec_kernel<4><<<(unsigned)u2_ceil_div(n_pts * (per_row / 4), 256), 256, 0, st>>>(g4, n_vox, per_row, idx, counts, o4, n_pts);
+        else if (per_row % 2 == 0)
+            voxelize_bwd_vec_kernel<2><<<(unsigned)u2_ceil_div(n_pts * (per_row / 2), 256), 256, 0, st>>>(g4, n_vox, per_row, idx, counts, o4, n_pts);
+        else
+            voxelize_bwd_vec_kernel<1><<<(unsigned)u2_ceil_div(n_pts * per_row, 256), 256, 0, st>>>(g4, n_vox, per_row, idx, counts, o4, n_pts);
+    } else {
+        voxelize_bwd_kernel<<<(unsigned)u2_ceil_div(n_pts * C, 256), 256, 0, st>>>(gout, n_vox, C, idx, counts, gfeats, n_pts);
+    }
     U2_LAUNCH_OK();
     return 0;
 }
@@ -300,12 +330,22 @@ __global__ void __launch_bounds__(256) devoxelize_bwd_kernel(const float4 *__res
         int cur[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { cur[k] = -1; acc[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        // the loads of point p + 1 are issued before point p is processed (the walk is serial: without the prefetch every
+        // point exposed a full global-load latency in front of its reductions)
+        int4 ni0 = __ldg(idx + 2 * p0), ni1 = __ldg(idx + 2 * p0 + 1);
+        float4 nw0 = __ldg(w + 2 * p0), nw1 = __ldg(w + 2 * p0 + 1);
+        float4 ng = __ldg(gout + p0 * V + v);
         for (int64_t p = p0; p < p1; p++) {
-            const int4 i0 = __ldg(idx + 2 * p), i1 = __ldg(idx + 2 * p + 1);
-            const float4 w0 = __ldg(w + 2 * p), w1 = __ldg(w + 2 * p + 1);
+            const int4 i0 = ni0, i1 = ni1;
+            const float4 w0 = nw0, w1 = nw1;
+            const float4 g = ng;
+            if (p + 1 < p1) {
+                ni0 = __ldg(idx + 2 * (p + 1)); ni1 = __ldg(idx + 2 * (p + 1) + 1);
+                nw0 = __ldg(w + 2 * (p + 1)); nw1 = __ldg(w + 2 * (p + 1) + 1);
+                ng = __ldg(gout + (p + 1) * V + v);
+            }
             const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
             const float wt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            const float4 g = __ldg(gout + p * V + v);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (id[k] < 0 || wt[k] == 0.f) continue;
