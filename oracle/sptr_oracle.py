@@ -1,7 +1,9 @@
 """CPU oracle of the SparseTransformer (`sptr`) window attention — TEST INFRASTRUCTURE, never imported by the product.
 
 Restates, in plain torch index arithmetic (any dtype, fp64 for gradient checks; autograd gives the backward), what
-third_party/SparseTransformer computes with its CUDA kernels.  Pins: the reference's own test for precompute_all holds a
+third_party/SparseTransformer computes with its CUDA kernels.  PINNED on the reference: tests/test_gpu_sptr_ref.py compares
+every function here with the reference's own kernels (oracle/_ref/libsptr_ref.so, compiled unmodified from /root/reference by
+oracle/Makefile).  CPU-side pins: the reference's own test for precompute_all holds a
 small known-answer case (third_party/SparseTransformer/test/test_precompute_all.py:9-19, 31-45, 67-70: counts [3, 2, 6]),
 checked in tests/test_sptr_cpu.py; the attention operators have no stored vectors in the reference (its tests compare two
 CUDA libraries on random data, test/test_attention_op_step1.py, test_relative_pos_encoding_op_step*.py), so for those the
