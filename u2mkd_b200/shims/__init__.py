@@ -169,9 +169,15 @@ def install_reference_shims() -> list:
         _module("torchpack", utils=utils)
         done.append("torchpack.utils.config")
     sptr = importlib.import_module("u2mkd_b200.sptr")
-    tp = sys.modules.get("third_party") or _module("third_party")
-    st = _module("third_party.SparseTransformer", sptr=sptr)
-    tp.SparseTransformer = st
+    # the import path the reference uses (spherical_transformer.py:7).  A real `third_party` package on sys.path (the
+    # reference checkout) is left alone — only the `sptr` leaf, whose own __init__ would import the absent `sptr_cuda`
+    # extension, is pre-seeded in sys.modules; without a checkout the two parent packages are stand-ins
+    if "third_party" not in sys.modules and _missing("third_party"):
+        _module("third_party")
+    if "third_party.SparseTransformer" not in sys.modules and _missing("third_party.SparseTransformer"):
+        st = _module("third_party.SparseTransformer", sptr=sptr)
+        if getattr(sys.modules.get("third_party"), "__u2_shim__", False):
+            sys.modules["third_party"].SparseTransformer = st
     sys.modules["third_party.SparseTransformer.sptr"] = sptr
     sys.modules.setdefault("sptr", sptr)
     done.append("third_party.SparseTransformer.sptr")
