@@ -285,7 +285,7 @@ int u2_syncbn_exchange(double *vals, int32_t len, const void *const *peer_bufs, 
  * and their backward kernels.  q (already scaled), k, v, out: fp32 [N, h, head_dim]; lse fp32 [N, h] (log-sum-exp of
  * every query's scores, saved for the backward); rel_idx int32 [M, 3] and table_{q,k,v} fp32 [L, 3, h, head_dim]
  * (contextual relative position encoding) or all four NULL (pe_type 'none').  head_dim 16 or 32, L <= 64.
- * The backward zeroes and accumulates dtable_*; dq / dk / dv are written once per row.                              */
+ * The backward writes dtable_* (per-block partials in `scratch`, then one fold); dq / dk / dv are written once per row.                              */
 int u2_window_attn_supported(int32_t head_dim, int32_t L);
 int u2_window_pairs(const int32_t *win_off, const int32_t *sq_off, int32_t n_windows, int32_t *index0_offsets,
                     int32_t *index1_offsets, int32_t *index0, int32_t *index1, u2_stream_t stream);
@@ -296,7 +296,9 @@ int u2_window_attn_bwd(const float *q, const float *k, const float *v, const int
                        int32_t n_windows, int32_t h, int32_t head_dim, const int32_t *rel_idx, const float *table_q,
                        const float *table_k, const float *table_v, int32_t L, const float *out, const float *lse,
                        const float *dout, float *dq, float *dk, float *dv, float *dtable_q, float *dtable_k,
-                       float *dtable_v, u2_stream_t stream);
+                       float *dtable_v, void *scratch, size_t scratch_bytes, u2_stream_t stream);
+/* scratch of the backward: one table-gradient partial per persistent block, folded by a second small kernel (0 without tables) */
+size_t u2_window_attn_bwd_scratch_bytes(int32_t n_windows, int32_t h, int32_t head_dim, int32_t L);
 
 /* ---- point <-> pixel transforms of the student's fusion path (pure-torch loops in the reference, no
  * native boundary there; these entries replace the bodies of

@@ -113,7 +113,8 @@ _SIGNATURES = {
     "u2_window_attn_supported": (ctypes.c_int, [_i32, _i32]),
     "u2_window_pairs": (ctypes.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p]),
     "u2_window_attn_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
-    "u2_window_attn_bwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "u2_window_attn_bwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "u2_window_attn_bwd_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "u2_kmap_pairs_scratch_bytes": (_sz, [_i64]),
     "u2_kmap_pairs": (ctypes.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "u2_conv_wgrad_pairs_supported": (ctypes.c_int, [_i32, _i32, _i32, _i32]),

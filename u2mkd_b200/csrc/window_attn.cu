@@ -16,8 +16,8 @@
 // Work split: block = (persistent slot, head), 64 threads; a thread owns one query (forward, backward pass A) or one key
 // (backward pass B) of the current window; keys / queries of the window stream through shared memory in chunks of 64
 // rows; the head's three tables (L x 3 x D floats each) stay in shared memory for the block's lifetime, and so do the
-// table-gradient accumulators of the backward (one flush of global atomics per block instead of one per thread as in the
-// reference).  fp32 throughout (the reference arithmetic); this path is bound by HBM / shared-memory traffic, not flops.
+// table-gradient accumulators of the backward (each persistent block writes ONE partial table with plain stores, a second
+// small kernel folds the partials — the reference adds 150 values per thread with global atomics).  fp32 throughout (the reference arithmetic); this path is bound by HBM / shared-memory traffic, not flops.
 #include <math.h>
 
 #include "u2_common.cuh"
@@ -38,6 +38,8 @@ struct WaParams {
     // backward
     const float *dout;
     float *dq, *dk, *dv, *dtq, *dtk, *dtv;
+    float *dtab_part;            // backward: per-block table-gradient partials [3][gridDim.x][L * 3][h][D]
+    int part_smem;               // backward: the block keeps its partial in shared memory and writes it once at the end
     int n_windows, h, L;
 };
 
@@ -139,20 +141,33 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_fwd_kernel(const WaPar
     }
 }
 
-// Backward.  Pass A (thread = query i): D_i = dO_i.O_i, dQ_i, dTq (+= ds q_i), dTv (+= p dO_i).
-//            Pass B (thread = key j)  : dK_j, dV_j, dTk (+= ds k_j).
+// Backward.  Pass A (thread = query i): D_i = dO_i.O_i, dQ_i, and the table gradients that are sums over a query's keys:
+//                dTq[r, a, :] += (sum_j ds_ij [r_a(i,j) = r]) q_i,   dTv[r, a, :] += (sum_j p_ij [r_a(i,j) = r]) dO_i.
+//            Pass B (thread = key j)  : dK_j, dV_j, dTk[r, a, :] += (sum_i ds_ij [r_a(i,j) = r]) k_j.
 // Both recompute s_ij and p_ij = exp(s_ij - lse_i); ds_ij = p_ij (dO_i.(v_j + tv_ij) - D_i).
+// Table gradients WITHOUT atomics: the bracketed sums are SCALAR histograms over the 3 L (row, axis) buckets, private to a
+// thread (shared memory, bucket-major so that the 64 threads of a bucket sit in 64 different banks: `+=` is a plain
+// read-modify-write); once the thread's keys are done the block folds  part[bucket][d] += sum_t H[bucket][t] * row_t[d]  —
+// a [3L x 64] x [64 x D] product in which every thread owns fixed outputs of the block's private slice of `dtab_part`.
+// (The first version added 9 x D floats per pair into shared accumulators with atomicAdd: fp32 shared atomics are CAS spin
+// loops, ATOMS.CAST.SPIN — 16 ms for 0.4 M pairs, 80 x the table-free kernel.)
 template <int D, bool REL>
 __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaParams p) {
     extern __shared__ __align__(16) float smem_f[];
     float *s_a = smem_f;                        // [CHUNK][D]  pass A: K chunk      pass B: Q chunk
     float *s_b = s_a + WA_CHUNK * D;            // [CHUNK][D]  pass A: V chunk      pass B: dO chunk
     float *s_c = s_b + WA_CHUNK * D;            // [CHUNK][2]  pass B: lse_i, D_i
-    float *s_tq = s_c + WA_CHUNK * 2;
-    const int TS = REL ? p.L * 3 * D : 0;
+    float *s_r0 = s_c + WA_CHUNK * 2;           // [THREADS][D] rows of the block's threads for the fold: q_i (A) / k_j (B)
+    float *s_r1 = s_r0 + WA_THREADS * D;        // [THREADS][D] dO_i (A)
+    float *s_tq = s_r1 + WA_THREADS * D;
+    const int TS = REL ? p.L * 3 * D : 0, LA = REL ? p.L * 3 : 0;
     float *s_tk = s_tq + TS, *s_tv = s_tk + TS;
-    float *s_gq = s_tv + TS, *s_gk = s_gq + TS, *s_gv = s_gk + TS;  // table-gradient accumulators
+    float *s_h0 = s_tv + TS;                    // [LA][THREADS] histogram of ds   (A: per query, B: per key)
+    float *s_h1 = s_h0 + LA * WA_THREADS;       // [LA][THREADS] histogram of p    (A)
+    float *s_part = s_h1 + LA * WA_THREADS;     // [3][TS] the block's table-gradient partial when it fits (p.part_smem)
     const int tid = threadIdx.x, head = blockIdx.y, C = p.h * D;
+    const size_t tab = (size_t)p.L * 3 * p.h * D, slice = (size_t)gridDim.x * tab;
+    float *part = REL ? p.dtab_part + (size_t)blockIdx.x * tab : nullptr;   // + t * slice for table t
     if (REL) {
         for (int e = tid; e < TS; e += WA_THREADS) {
             const int d = e % D, la = e / D;
@@ -160,10 +175,26 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
             s_tq[e] = __ldg(p.tq + g);
             s_tk[e] = __ldg(p.tk + g);
             s_tv[e] = __ldg(p.tv + g);
-            s_gq[e] = 0.f; s_gk[e] = 0.f; s_gv[e] = 0.f;
+            // the same thread owns these outputs in every fold
+            if (p.part_smem) { s_part[e] = 0.f; s_part[TS + e] = 0.f; s_part[2 * TS + e] = 0.f; }
+            else { part[g] = 0.f; part[slice + g] = 0.f; part[2 * slice + g] = 0.f; }
         }
+        for (int e = tid; e < LA * WA_THREADS; e += WA_THREADS) { s_h0[e] = 0.f; s_h1[e] = 0.f; }
     }
     __syncthreads();
+    // part[t][bucket][d] += sum over the block's live threads of H[bucket][thread] * rows[thread][d]; zeroes H on the way out
+    auto fold = [&](float *H, const float *rows, int n_live, int t) {
+        for (int e = tid; e < TS; e += WA_THREADS) {
+            const int d = e % D, la = e / D;
+            const float *hrow = H + la * WA_THREADS;
+            float acc = 0.f;
+            for (int i = 0; i < n_live; i++) acc = fmaf(hrow[i], rows[i * D + d], acc);
+            if (p.part_smem) s_part[t * TS + e] += acc;
+            else if (acc != 0.f) part[t * slice + ((size_t)la * p.h + head) * D + d] += acc;
+        }
+        __syncthreads();
+        for (int la = 0; la < LA; la++) H[la * WA_THREADS + tid] = 0.f;   // own column only
+    };
     for (int w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
         const int start = __ldg(p.win_off + w), nw = __ldg(p.win_off + w + 1) - start;
         const long long sq = __ldg(p.sq_off + w);
@@ -184,6 +215,10 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
 #pragma unroll
                 for (int d = 0; d < D; d++) Di = fmaf(go[d], o[d], Di);
                 lse = __ldg(p.lse + (size_t)(start + i) * p.h + head);
+                if (REL) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) { s_r0[tid * D + d] = q[d]; s_r1[tid * D + d] = go[d]; }
+                }
             }
             for (int j0 = 0; j0 < nw; j0 += WA_CHUNK) {
                 const int nj = min(WA_CHUNK, nw - j0);
@@ -225,14 +260,9 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
 #pragma unroll
                     for (int d = 0; d < D; d++) dq[d] = fmaf(ds, REL ? kj[d] + tq[d] : kj[d], dq[d]);
                     if (REL) {
-                        float *gq0 = s_gq + (r0 * 3 + 0) * D, *gq1 = s_gq + (r1 * 3 + 1) * D, *gq2 = s_gq + (r2 * 3 + 2) * D;
-                        float *gv0 = s_gv + (r0 * 3 + 0) * D, *gv1 = s_gv + (r1 * 3 + 1) * D, *gv2 = s_gv + (r2 * 3 + 2) * D;
-#pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            const float a = ds * q[d], b = pj * go[d];
-                            atomicAdd(gq0 + d, a); atomicAdd(gq1 + d, a); atomicAdd(gq2 + d, a);
-                            atomicAdd(gv0 + d, b); atomicAdd(gv1 + d, b); atomicAdd(gv2 + d, b);
-                        }
+                        const int b0 = (r0 * 3 + 0) * WA_THREADS + tid, b1 = (r1 * 3 + 1) * WA_THREADS + tid, b2 = (r2 * 3 + 2) * WA_THREADS + tid;
+                        s_h0[b0] += ds; s_h0[b1] += ds; s_h0[b2] += ds;
+                        s_h1[b0] += pj; s_h1[b1] += pj; s_h1[b2] += pj;
                     }
                 }
             }
@@ -240,6 +270,13 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
                 float *op = p.dq + (size_t)(start + i) * C + head * D;
 #pragma unroll
                 for (int d = 0; d < D; d += 4) *reinterpret_cast<float4 *>(op + d) = make_float4(dq[d], dq[d + 1], dq[d + 2], dq[d + 3]);
+            }
+            if (REL) {
+                const int n_live = min(WA_THREADS, nw - i0);
+                __syncthreads();
+                fold(s_h0, s_r0, n_live, 0);   // dTq += Hds x q
+                fold(s_h1, s_r1, n_live, 2);   // dTv += Hp  x dO
+                __syncthreads();
             }
         }
         // ---------------- pass B: columns (keys) ----------------
@@ -252,6 +289,10 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
             if (live) {
                 load_row<D>(kk, p.k + (size_t)(start + j) * C + head * D);
                 load_row<D>(vv, p.v + (size_t)(start + j) * C + head * D);
+                if (REL) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) s_r0[tid * D + d] = kk[d];
+                }
             }
             for (int i0 = 0; i0 < nw; i0 += WA_CHUNK) {
                 const int ni = min(WA_CHUNK, nw - i0);
@@ -299,12 +340,9 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
                         dv[d] = fmaf(pj, gi[d], dv[d]);
                     }
                     if (REL) {
-                        float *g0 = s_gk + (r0 * 3 + 0) * D, *g1 = s_gk + (r1 * 3 + 1) * D, *g2 = s_gk + (r2 * 3 + 2) * D;
-#pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            const float a = ds * kk[d];
-                            atomicAdd(g0 + d, a); atomicAdd(g1 + d, a); atomicAdd(g2 + d, a);
-                        }
+                        s_h0[(r0 * 3 + 0) * WA_THREADS + tid] += ds;
+                        s_h0[(r1 * 3 + 1) * WA_THREADS + tid] += ds;
+                        s_h0[(r2 * 3 + 2) * WA_THREADS + tid] += ds;
                     }
                 }
             }
@@ -316,18 +354,36 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
                     *reinterpret_cast<float4 *>(ov + d) = make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]);
                 }
             }
+            if (REL) {
+                const int n_live = min(WA_THREADS, nw - j0);
+                __syncthreads();
+                fold(s_h0, s_r0, n_live, 1);   // dTk += Hds x k
+                __syncthreads();
+            }
         }
     }
-    if (REL) {
-        __syncthreads();
+    if (REL && p.part_smem) {
         for (int e = tid; e < TS; e += WA_THREADS) {
-            const int d = e % D, la = e / D;
-            const size_t g = ((size_t)la * p.h + head) * D + d;
-            if (s_gq[e] != 0.f) atomicAdd(p.dtq + g, s_gq[e]);
-            if (s_gk[e] != 0.f) atomicAdd(p.dtk + g, s_gk[e]);
-            if (s_gv[e] != 0.f) atomicAdd(p.dtv + g, s_gv[e]);
+            const size_t g = ((size_t)(e / D) * p.h + head) * D + e % D;
+            part[g] = s_part[e]; part[slice + g] = s_part[TS + e]; part[2 * slice + g] = s_part[2 * TS + e];
         }
     }
+}
+
+// dtable_{q,k,v}[e] = sum over the blocks' partials
+__global__ void __launch_bounds__(256) window_attn_tab_reduce_kernel(const float *__restrict__ part, int n_blocks, size_t tab,
+                                                                      float *__restrict__ dtq, float *__restrict__ dtk, float *__restrict__ dtv) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= tab) return;
+    const int t = blockIdx.y;
+    const float *src = part + (size_t)t * n_blocks * tab + e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = 0;
+    for (; b + 3 < n_blocks; b += 4) {
+        s0 += src[(size_t)b * tab]; s1 += src[(size_t)(b + 1) * tab]; s2 += src[(size_t)(b + 2) * tab]; s3 += src[(size_t)(b + 3) * tab];
+    }
+    for (; b < n_blocks; b++) s0 += src[(size_t)b * tab];
+    (t == 0 ? dtq : (t == 1 ? dtk : dtv))[e] = (s0 + s1) + (s2 + s3);
 }
 
 // index_0 / index_1 / offsets of every (query, key) pair, the layout precompute_all defines
@@ -346,6 +402,14 @@ __global__ void __launch_bounds__(256) window_pairs_kernel(const int *__restrict
             index1[sq + e] = start + e % nw;
         }
     }
+}
+
+// backward: its shared memory (tables + two per-thread bucket histograms + the block's partial, 100-200 KB) admits one block
+// per SM; more blocks than fit only add table-gradient partials to fold
+int grid_x_bwd(int n_windows, int h) {
+    int g = (U2_NUM_SMS + h - 1) / h;
+    if (g < 1) g = 1;
+    return g < n_windows ? g : n_windows;
 }
 
 int grid_x(int n_windows, int h) {
@@ -378,10 +442,21 @@ static int wa_launch_fwd(const WaParams &p, cudaStream_t st) {
 
 template <int D, bool REL>
 static int wa_launch_bwd(const WaParams &p, cudaStream_t st) {
-    const size_t smem = (size_t)(2 * WA_CHUNK * D + 2 * WA_CHUNK + (REL ? 6 * p.L * 3 * D : 0)) * sizeof(float);
+    size_t smem = (size_t)(2 * WA_CHUNK * D + 2 * WA_CHUNK + 2 * WA_THREADS * D +
+                           (REL ? 3 * p.L * 3 * D + 2 * p.L * 3 * WA_THREADS : 0)) * sizeof(float);
+    WaParams q = p;
+    const size_t part_bytes = REL ? (size_t)3 * p.L * 3 * D * sizeof(float) : 0;
+    q.part_smem = REL && smem + part_bytes <= 200 * 1024;   // else the folds add straight into the block's global slice
+    if (q.part_smem) smem += part_bytes;
     U2_CUDA_OK(cudaFuncSetAttribute(window_attn_bwd_kernel<D, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    window_attn_bwd_kernel<D, REL><<<dim3(grid_x(p.n_windows, p.h), p.h), WA_THREADS, smem, st>>>(p);
+    const int gx = REL ? grid_x_bwd(p.n_windows, p.h) : grid_x(p.n_windows, p.h);
+    window_attn_bwd_kernel<D, REL><<<dim3(gx, p.h), WA_THREADS, smem, st>>>(q);
     U2_LAUNCH_OK();
+    if (REL) {
+        const size_t tab = (size_t)p.L * 3 * p.h * D;
+        window_attn_tab_reduce_kernel<<<dim3((unsigned)u2_ceil_div((int64_t)tab, 256), 3), 256, 0, st>>>(p.dtab_part, gx, tab, p.dtq, p.dtk, p.dtv);
+        U2_LAUNCH_OK();
+    }
     return 0;
 }
 
@@ -407,11 +482,16 @@ extern "C" int u2_window_attn_fwd(const float *q, const float *k, const float *v
     return rel_idx ? wa_launch_fwd<32, true>(p, st) : wa_launch_fwd<32, false>(p, st);
 }
 
+extern "C" size_t u2_window_attn_bwd_scratch_bytes(int32_t n_windows, int32_t h, int32_t head_dim, int32_t L) {
+    if (L <= 0 || n_windows <= 0) return 0;
+    return (size_t)3 * grid_x_bwd(n_windows, h) * (size_t)L * 3 * h * head_dim * sizeof(float);
+}
+
 extern "C" int u2_window_attn_bwd(const float *q, const float *k, const float *v, const int32_t *win_off, const int32_t *sq_off,
                                   int32_t n_windows, int32_t h, int32_t head_dim, const int32_t *rel_idx, const float *table_q,
                                   const float *table_k, const float *table_v, int32_t L, const float *out, const float *lse,
                                   const float *dout, float *dq, float *dk, float *dv, float *dtable_q, float *dtable_k,
-                                  float *dtable_v, u2_stream_t stream) {
+                                  float *dtable_v, void *scratch, size_t scratch_bytes, u2_stream_t stream) {
     WaParams p = {};
     p.q = q; p.k = k; p.v = v; p.win_off = win_off; p.sq_off = sq_off; p.rel = rel_idx; p.tq = table_q; p.tk = table_k; p.tv = table_v;
     p.out = const_cast<float *>(out); p.lse = const_cast<float *>(lse); p.dout = dout; p.dq = dq; p.dk = dk; p.dv = dv;
@@ -419,11 +499,16 @@ extern "C" int u2_window_attn_bwd(const float *q, const float *k, const float *v
     if (wa_check(p, head_dim, "u2_window_attn_bwd")) return 1;
     U2_CHECK_ARG(dout && dq && dk && dv && (!rel_idx || (dtable_q && dtable_k && dtable_v)), "u2_window_attn_bwd: null gradient pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (rel_idx) {  // the blocks add their table gradients with atomics
-        const size_t tb = (size_t)L * 3 * h * head_dim * sizeof(float);
-        U2_CUDA_OK(cudaMemsetAsync(dtable_q, 0, tb, st));
-        U2_CUDA_OK(cudaMemsetAsync(dtable_k, 0, tb, st));
-        U2_CUDA_OK(cudaMemsetAsync(dtable_v, 0, tb, st));
+    if (rel_idx) {
+        U2_CHECK_ARG(n_windows <= 0 || (scratch && scratch_bytes >= u2_window_attn_bwd_scratch_bytes(n_windows, h, head_dim, L)),
+                     "u2_window_attn_bwd: scratch too small (u2_window_attn_bwd_scratch_bytes)");
+        p.dtab_part = (float *)scratch;
+        if (n_windows <= 0) {  // nothing to fold: the table gradients are zero
+            const size_t tb = (size_t)L * 3 * h * head_dim * sizeof(float);
+            U2_CUDA_OK(cudaMemsetAsync(dtable_q, 0, tb, st));
+            U2_CUDA_OK(cudaMemsetAsync(dtable_k, 0, tb, st));
+            U2_CUDA_OK(cudaMemsetAsync(dtable_v, 0, tb, st));
+        }
     }
     if (n_windows <= 0) return 0;
     if (head_dim == 16) return rel_idx ? wa_launch_bwd<16, true>(p, st) : wa_launch_bwd<16, false>(p, st);

@@ -126,12 +126,15 @@ class WindowAttentionFn(Function):
         dtq = torch.empty_like(tq) if rel else None
         dtk = torch.empty_like(tk) if rel else None
         dtv = torch.empty_like(tv) if rel else None
+        L = tq.shape[0] if rel else 0
+        sbytes = lib().u2_window_attn_bwd_scratch_bytes(ctx.n_windows, h, d, L)
+        scratch = ops._ws("wattn", sbytes, q.device) if sbytes else None
         check(lib().u2_window_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), win_off.data_ptr(), sq_off.data_ptr(),
                                        ctx.n_windows, h, d, ops._ptr(rel_idx), ops._ptr(tq), ops._ptr(tk), ops._ptr(tv),
-                                       tq.shape[0] if rel else 0, out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
+                                       L, out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
                                        dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ops._ptr(dtq), ops._ptr(dtk), ops._ptr(dtv),
-                                       ops._st()))
-        ops._count(1 + (3 if rel else 0))
+                                       ops._ptr(scratch), scratch.numel() if scratch is not None else 0, ops._st()))
+        ops._count(2 if rel else 1)
         return dq, dk, dv, dtq, dtk, dtv, None, None, None, None
 
 
