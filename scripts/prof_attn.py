@@ -11,7 +11,7 @@ def run(n_pts, mean_len, h, L=47, d=16, tag="", rel_on=True):
     tabs = [torch.randn(L, 3, h, d, device="cuda", requires_grad=True) for _ in range(3)]
     rel = torch.randint(0, L, (M, 3), device="cuda", dtype=torch.int32)
     wo, so_ = F.window_offsets(counts.cuda())
-    for rep in range(2):
+    for rep in range(4):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         o = F.window_attention(q, k, v, wo, so_, counts.shape[0], rel, *tabs) if rel_on else F.window_attention(q, k, v, wo, so_, counts.shape[0])
@@ -28,3 +28,7 @@ run(2700, 32, 8, tag="s4 sphere")
 run(67000, 100, 1, tag="big win  ")
 run(67000, 5, 1, tag="s1 cubic  no tables", rel_on=False)
 run(67000, 24, 1, tag="s1 sphere no tables", rel_on=False)
+run(67000, 5, 1, tag="s1 cubic (again)")
+run(67000, 3, 1, tag="tiny windows")
+run(67000, 8, 1, tag="windows of 8")
+run(67000, 5, 1, L=9, tag="s1 cubic L=9")

@@ -54,10 +54,16 @@ __device__ __forceinline__ void load_row(float (&r)[D], const float *p) {
 
 // sum of the three table rows selected by (r0, r1, r2) for one head: T[r_a, a, :]
 template <int D>
-__device__ __forceinline__ void table_sum(float (&t)[D], const float *s_tab, int r0, int r1, int r2) {
-    const float *a = s_tab + (r0 * 3 + 0) * D, *b = s_tab + (r1 * 3 + 1) * D, *c = s_tab + (r2 * 3 + 2) * D;
+__device__ __forceinline__ void table_sum(float (&t)[D], const float *s_tab, int r0, int r1, int r2, int stride = D) {
+    const float *a = s_tab + (r0 * 3 + 0) * stride, *b = s_tab + (r1 * 3 + 1) * stride, *c = s_tab + (r2 * 3 + 2) * stride;
 #pragma unroll
     for (int d = 0; d < D; d++) t[d] = a[d] + b[d] + c[d];
+}
+
+template <int D>
+__device__ __forceinline__ void store_row(float *p, const float (&r)[D]) {
+#pragma unroll
+    for (int d = 0; d < D; d += 4) *reinterpret_cast<float4 *>(p + d) = make_float4(r[d], r[d + 1], r[d + 2], r[d + 3]);
 }
 
 template <int D, bool REL>
@@ -141,35 +147,60 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_fwd_kernel(const WaPar
     }
 }
 
-// Backward.  Pass A (thread = query i): D_i = dO_i.O_i, dQ_i, and the table gradients that are sums over a query's keys:
+// Backward.  Pass A (rows = queries i): D_i = dO_i.O_i, dQ_i, and the table gradients that are sums over a query's keys:
 //                dTq[r, a, :] += (sum_j ds_ij [r_a(i,j) = r]) q_i,   dTv[r, a, :] += (sum_j p_ij [r_a(i,j) = r]) dO_i.
-//            Pass B (thread = key j)  : dK_j, dV_j, dTk[r, a, :] += (sum_i ds_ij [r_a(i,j) = r]) k_j.
+//            Pass B (rows = keys j)   : dK_j, dV_j, dTk[r, a, :] += (sum_i ds_ij [r_a(i,j) = r]) k_j.
 // Both recompute s_ij and p_ij = exp(s_ij - lse_i); ds_ij = p_ij (dO_i.(v_j + tv_ij) - D_i).
+// Work layout: a block owns a contiguous range of windows holding ~1/gridDim.x of the PAIRS and walks it in groups of up to
+// WB_ROWS (64) rows — several small windows packed together, or one larger window in 64-row pieces.  A row is served by a QUAD
+// of lanes, each owning D/4 of the channels (dot products finish with two quad shuffles), so a group keeps 256 threads busy
+// whatever the window size (the first version ran one window per 64-thread pass: 5 live threads on the cubic windows).
 // Table gradients WITHOUT atomics: the bracketed sums are SCALAR histograms over the 3 L (row, axis) buckets, private to a
-// thread (shared memory, bucket-major so that the 64 threads of a bucket sit in 64 different banks: `+=` is a plain
-// read-modify-write); once the thread's keys are done the block folds  part[bucket][d] += sum_t H[bucket][t] * row_t[d]  —
-// a [3L x 64] x [64 x D] product in which every thread owns fixed outputs of the block's private slice of `dtab_part`.
-// (The first version added 9 x D floats per pair into shared accumulators with atomicAdd: fp32 shared atomics are CAS spin
-// loops, ATOMS.CAST.SPIN — 16 ms for 0.4 M pairs, 80 x the table-free kernel.)
+// row (shared memory, H[bucket][row]; lane a of the quad updates axis a, `+=` is a plain read-modify-write); when the group's
+// pairs are done the block folds  part[bucket][d] += sum_row H[bucket][row] * x_row[d]  — a [3L x 64] x [64 x D] product in
+// which every thread owns fixed outputs of the block's partial (shared memory when it fits, else its slice of `dtab_part`).
+// (Adding 9 x D floats per pair into shared accumulators with atomicAdd is 80 x slower than the table-free kernel: fp32
+// shared atomics are CAS spin loops, ATOMS.CAST.SPIN.)
+constexpr int WB_ROWS = 64, WB_THREADS = WB_ROWS * 4;
+
+__device__ __forceinline__ float quad_sum(float x, unsigned mask) {
+    x += __shfl_xor_sync(mask, x, 1);
+    x += __shfl_xor_sync(mask, x, 2);
+    return x;
+}
+
+// first w in [0, n] with off[w] >= target (off is non-decreasing, off[n] is the total)
+__device__ __forceinline__ int first_window_at(const int *off, int n, long long target) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)__ldg(off + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 template <int D, bool REL>
-__global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaParams p) {
+__global__ void __launch_bounds__(WB_THREADS) window_attn_bwd_kernel(const WaParams p) {
+    constexpr int DL = D / 4;                    // channels of a row owned by one lane of its quad
     extern __shared__ __align__(16) float smem_f[];
-    float *s_a = smem_f;                        // [CHUNK][D]  pass A: K chunk      pass B: Q chunk
-    float *s_b = s_a + WA_CHUNK * D;            // [CHUNK][D]  pass A: V chunk      pass B: dO chunk
-    float *s_c = s_b + WA_CHUNK * D;            // [CHUNK][2]  pass B: lse_i, D_i
-    float *s_r0 = s_c + WA_CHUNK * 2;           // [THREADS][D] rows of the block's threads for the fold: q_i (A) / k_j (B)
-    float *s_r1 = s_r0 + WA_THREADS * D;        // [THREADS][D] dO_i (A)
-    float *s_tq = s_r1 + WA_THREADS * D;
+    float *s_a = smem_f;                        // [ROWS][D]  pass A: K chunk      pass B: Q chunk
+    float *s_b = s_a + WB_ROWS * D;             // [ROWS][D]  pass A: V chunk      pass B: dO chunk
+    float *s_c = s_b + WB_ROWS * D;             // [ROWS][2]  pass B: lse_i, D_i
+    float *s_r0 = s_c + WB_ROWS * 2;            // [ROWS][D]  the group's own rows for the fold: q_i (A) / k_j (B)
+    float *s_r1 = s_r0 + WB_ROWS * D;           // [ROWS][D]  dO_i (A)
+    float *s_tq = s_r1 + WB_ROWS * D;
     const int TS = REL ? p.L * 3 * D : 0, LA = REL ? p.L * 3 : 0;
     float *s_tk = s_tq + TS, *s_tv = s_tk + TS;
-    float *s_h0 = s_tv + TS;                    // [LA][THREADS] histogram of ds   (A: per query, B: per key)
-    float *s_h1 = s_h0 + LA * WA_THREADS;       // [LA][THREADS] histogram of p    (A)
-    float *s_part = s_h1 + LA * WA_THREADS;     // [3][TS] the block's table-gradient partial when it fits (p.part_smem)
+    float *s_h0 = s_tv + TS;                    // [LA][ROWS] histogram of ds   (A: per query, B: per key)
+    float *s_h1 = s_h0 + LA * WB_ROWS;          // [LA][ROWS] histogram of p    (A)
+    float *s_part = s_h1 + LA * WB_ROWS;        // [3][TS] the block's table-gradient partial when it fits (p.part_smem)
     const int tid = threadIdx.x, head = blockIdx.y, C = p.h * D;
+    const int rs = tid >> 2, c = tid & 3, c0 = c * DL;   // row slot, lane of the quad, first owned channel
+    const unsigned qmask = 0xFu << ((tid & 31) & ~3);
     const size_t tab = (size_t)p.L * 3 * p.h * D, slice = (size_t)gridDim.x * tab;
     float *part = REL ? p.dtab_part + (size_t)blockIdx.x * tab : nullptr;   // + t * slice for table t
     if (REL) {
-        for (int e = tid; e < TS; e += WA_THREADS) {
+        for (int e = tid; e < TS; e += WB_THREADS) {
             const int d = e % D, la = e / D;
             const size_t g = ((size_t)la * p.h + head) * D + d;
             s_tq[e] = __ldg(p.tq + g);
@@ -179,191 +210,203 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_bwd_kernel(const WaPar
             if (p.part_smem) { s_part[e] = 0.f; s_part[TS + e] = 0.f; s_part[2 * TS + e] = 0.f; }
             else { part[g] = 0.f; part[slice + g] = 0.f; part[2 * slice + g] = 0.f; }
         }
-        for (int e = tid; e < LA * WA_THREADS; e += WA_THREADS) { s_h0[e] = 0.f; s_h1[e] = 0.f; }
+        for (int e = tid; e < LA * WB_ROWS; e += WB_THREADS) { s_h0[e] = 0.f; s_h1[e] = 0.f; }
     }
     __syncthreads();
-    // part[t][bucket][d] += sum over the block's live threads of H[bucket][thread] * rows[thread][d]; zeroes H on the way out
-    auto fold = [&](float *H, const float *rows, int n_live, int t) {
-        for (int e = tid; e < TS; e += WA_THREADS) {
+    // part[t][bucket][d] += sum over the group's rows of H[bucket][row] * rows[row][d]; leaves H zeroed
+    auto fold = [&](float *H, const float *rows, int n_rows, int t) {
+        for (int e = tid; e < TS; e += WB_THREADS) {
             const int d = e % D, la = e / D;
-            const float *hrow = H + la * WA_THREADS;
+            const float *hrow = H + la * WB_ROWS;
             float acc = 0.f;
-            for (int i = 0; i < n_live; i++) acc = fmaf(hrow[i], rows[i * D + d], acc);
+            for (int i = 0; i < n_rows; i++) acc = fmaf(hrow[i], rows[i * D + d], acc);
             if (p.part_smem) s_part[t * TS + e] += acc;
             else if (acc != 0.f) part[t * slice + ((size_t)la * p.h + head) * D + d] += acc;
         }
         __syncthreads();
-        for (int la = 0; la < LA; la++) H[la * WA_THREADS + tid] = 0.f;   // own column only
+        for (int e = tid; e < LA * WB_ROWS; e += WB_THREADS) H[e] = 0.f;
     };
-    for (int w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
-        const int start = __ldg(p.win_off + w), nw = __ldg(p.win_off + w + 1) - start;
-        const long long sq = __ldg(p.sq_off + w);
-        // ---------------- pass A: rows (queries) ----------------
-        for (int i0 = 0; i0 < nw; i0 += WA_THREADS) {
-            const int i = i0 + tid;
-            const bool live = i < nw;
-            float q[D], go[D], dq[D];
-            float lse = 0.f, Di = 0.f;
+    // the block's windows: [wb, we) holds the pairs [b, b + 1) * M / gridDim.x
+    const long long M = __ldg(p.sq_off + p.n_windows);
+    const int wb = blockIdx.x == 0 ? 0 : first_window_at(p.sq_off, p.n_windows, M * blockIdx.x / gridDim.x);
+    const int we = blockIdx.x + 1 == gridDim.x ? p.n_windows : first_window_at(p.sq_off, p.n_windows, M * (blockIdx.x + 1) / gridDim.x);
+    for (int w0 = wb; w0 < we;) {
+        // group = windows [w0, w1): as many as fit WB_ROWS rows (always at least one)
+        const int gs = __ldg(p.win_off + w0);
+        int w1 = w0 + 1;
+        while (w1 < we && __ldg(p.win_off + w1 + 1) - gs <= WB_ROWS) w1++;
+        const int grows = __ldg(p.win_off + w1) - gs;    // > WB_ROWS only for a single large window
+        // both passes: rows of the group in 64-row pieces (i0), the others of a row's window in 64-row chunks (j0)
+        for (int i0 = 0; i0 < grows; i0 += WB_ROWS) {
+            const int row = gs + i0 + rs;
+            const bool live = row < gs + grows;
+            int mw = w0;
+            if (live) for (int w = w0 + 1; w < w1 && row >= __ldg(p.win_off + w); w++) mw = w;
+            const int ws = __ldg(p.win_off + mw), nw = __ldg(p.win_off + mw + 1) - ws, il = row - ws;
+            const long long sq = __ldg(p.sq_off + mw);
+            const int n_rows = min(WB_ROWS, grows - i0);
+            // ---------------- pass A: the row is a query ----------------
+            {
+                float q[DL], go[DL], dq[DL];
+                float lse = 0.f, Di = 0.f;
 #pragma unroll
-            for (int d = 0; d < D; d++) dq[d] = 0.f;
-            if (live) {
-                const size_t row = (size_t)(start + i) * C + head * D;
-                load_row<D>(q, p.q + row);
-                load_row<D>(go, p.dout + row);
-                float o[D];
-                load_row<D>(o, p.out + row);
+                for (int d = 0; d < DL; d++) dq[d] = 0.f;
+                if (live) {
+                    const size_t g = (size_t)row * C + head * D + c0;
+                    float o[DL];
+                    load_row<DL>(q, p.q + g);
+                    load_row<DL>(go, p.dout + g);
+                    load_row<DL>(o, p.out + g);
 #pragma unroll
-                for (int d = 0; d < D; d++) Di = fmaf(go[d], o[d], Di);
-                lse = __ldg(p.lse + (size_t)(start + i) * p.h + head);
-                if (REL) {
-#pragma unroll
-                    for (int d = 0; d < D; d++) { s_r0[tid * D + d] = q[d]; s_r1[tid * D + d] = go[d]; }
-                }
-            }
-            for (int j0 = 0; j0 < nw; j0 += WA_CHUNK) {
-                const int nj = min(WA_CHUNK, nw - j0);
-                __syncthreads();
-                if (tid < nj) {
-                    float r[D];
-                    load_row<D>(r, p.k + (size_t)(start + j0 + tid) * C + head * D);
-#pragma unroll
-                    for (int d = 0; d < D; d++) s_a[tid * D + d] = r[d];
-                    load_row<D>(r, p.v + (size_t)(start + j0 + tid) * C + head * D);
-#pragma unroll
-                    for (int d = 0; d < D; d++) s_b[tid * D + d] = r[d];
-                }
-                __syncthreads();
-                if (!live) continue;
-                const int *rel = REL ? p.rel + (sq + (long long)i * nw + j0) * 3 : nullptr;
-                for (int j = 0; j < nj; j++) {
-                    const float *kj = s_a + j * D, *vj = s_b + j * D;
-                    float s = 0.f, dp = 0.f;
-                    float tq[D];
-                    int r0 = 0, r1 = 0, r2 = 0;
+                    for (int d = 0; d < DL; d++) Di = fmaf(go[d], o[d], Di);
+                    Di = quad_sum(Di, qmask);
+                    lse = __ldg(p.lse + (size_t)row * p.h + head);
                     if (REL) {
-                        r0 = __ldg(rel + 3 * j); r1 = __ldg(rel + 3 * j + 1); r2 = __ldg(rel + 3 * j + 2);
-                        float tk[D], tv[D];
-                        table_sum<D>(tq, s_tq, r0, r1, r2);
-                        table_sum<D>(tk, s_tk, r0, r1, r2);
-                        table_sum<D>(tv, s_tv, r0, r1, r2);
 #pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            s = fmaf(q[d], kj[d] + tq[d], fmaf(kj[d], tk[d], s));
-                            dp = fmaf(go[d], vj[d] + tv[d], dp);
+                        for (int d = 0; d < DL; d++) { s_r0[rs * D + c0 + d] = q[d]; s_r1[rs * D + c0 + d] = go[d]; }
+                    }
+                }
+                for (int j0 = 0; j0 < grows; j0 += WB_ROWS) {
+                    const int nj = min(WB_ROWS, grows - j0);
+                    __syncthreads();
+                    if (rs < nj) {
+                        const size_t g = (size_t)(gs + j0 + rs) * C + head * D + c0;
+                        float r[DL];
+                        load_row<DL>(r, p.k + g);
+#pragma unroll
+                        for (int d = 0; d < DL; d++) s_a[rs * D + c0 + d] = r[d];
+                        load_row<DL>(r, p.v + g);
+#pragma unroll
+                        for (int d = 0; d < DL; d++) s_b[rs * D + c0 + d] = r[d];
+                    }
+                    __syncthreads();
+                    if (!live) continue;
+                    // the keys of my window inside this chunk
+                    const int jb = max(ws - (gs + j0), 0), je = min(ws + nw - (gs + j0), nj);
+                    const int *rel = REL ? p.rel + (sq + (long long)il * nw + (gs + j0 - ws)) * 3 : nullptr;
+                    for (int j = jb; j < je; j++) {
+                        const float *kj = s_a + j * D + c0, *vj = s_b + j * D + c0;
+                        float s = 0.f, dp = 0.f;
+                        float tq[DL];
+                        int r0 = 0, r1 = 0, r2 = 0;
+                        if (REL) {
+                            r0 = __ldg(rel + 3 * j); r1 = __ldg(rel + 3 * j + 1); r2 = __ldg(rel + 3 * j + 2);
+                            float tk[DL], tv[DL];
+                            table_sum<DL>(tq, s_tq + c0, r0, r1, r2, D);
+                            table_sum<DL>(tk, s_tk + c0, r0, r1, r2, D);
+                            table_sum<DL>(tv, s_tv + c0, r0, r1, r2, D);
+#pragma unroll
+                            for (int d = 0; d < DL; d++) {
+                                s = fmaf(q[d], kj[d] + tq[d], fmaf(kj[d], tk[d], s));
+                                dp = fmaf(go[d], vj[d] + tv[d], dp);
+                            }
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < DL; d++) { s = fmaf(q[d], kj[d], s); dp = fmaf(go[d], vj[d], dp); }
                         }
-                    } else {
+                        s = quad_sum(s, qmask);
+                        dp = quad_sum(dp, qmask);
+                        const float pj = __expf(s - lse);
+                        const float ds = pj * (dp - Di);
 #pragma unroll
-                        for (int d = 0; d < D; d++) { s = fmaf(q[d], kj[d], s); dp = fmaf(go[d], vj[d], dp); }
-                    }
-                    const float pj = __expf(s - lse);
-                    const float ds = pj * (dp - Di);
-#pragma unroll
-                    for (int d = 0; d < D; d++) dq[d] = fmaf(ds, REL ? kj[d] + tq[d] : kj[d], dq[d]);
-                    if (REL) {
-                        const int b0 = (r0 * 3 + 0) * WA_THREADS + tid, b1 = (r1 * 3 + 1) * WA_THREADS + tid, b2 = (r2 * 3 + 2) * WA_THREADS + tid;
-                        s_h0[b0] += ds; s_h0[b1] += ds; s_h0[b2] += ds;
-                        s_h1[b0] += pj; s_h1[b1] += pj; s_h1[b2] += pj;
+                        for (int d = 0; d < DL; d++) dq[d] = fmaf(ds, REL ? kj[d] + tq[d] : kj[d], dq[d]);
+                        if (REL && c < 3) {   // lane a of the quad keeps axis a
+                            const int bkt = ((c == 0 ? r0 : c == 1 ? r1 : r2) * 3 + c) * WB_ROWS + rs;
+                            s_h0[bkt] += ds;
+                            s_h1[bkt] += pj;
+                        }
                     }
                 }
+                if (live) store_row<DL>(p.dq + (size_t)row * C + head * D + c0, dq);
+                if (REL) {
+                    __syncthreads();
+                    fold(s_h0, s_r0, n_rows, 0);   // dTq += Hds x q
+                    fold(s_h1, s_r1, n_rows, 2);   // dTv += Hp  x dO
+                }
             }
-            if (live) {
-                float *op = p.dq + (size_t)(start + i) * C + head * D;
+            // ---------------- pass B: the row is a key ----------------
+            {
+                float kk[DL], vv[DL], dk[DL], dv[DL];
 #pragma unroll
-                for (int d = 0; d < D; d += 4) *reinterpret_cast<float4 *>(op + d) = make_float4(dq[d], dq[d + 1], dq[d + 2], dq[d + 3]);
-            }
-            if (REL) {
-                const int n_live = min(WA_THREADS, nw - i0);
-                __syncthreads();
-                fold(s_h0, s_r0, n_live, 0);   // dTq += Hds x q
-                fold(s_h1, s_r1, n_live, 2);   // dTv += Hp  x dO
-                __syncthreads();
+                for (int d = 0; d < DL; d++) { dk[d] = 0.f; dv[d] = 0.f; }
+                if (live) {
+                    const size_t g = (size_t)row * C + head * D + c0;
+                    load_row<DL>(kk, p.k + g);
+                    load_row<DL>(vv, p.v + g);
+                    if (REL) {
+#pragma unroll
+                        for (int d = 0; d < DL; d++) s_r0[rs * D + c0 + d] = kk[d];
+                    }
+                }
+                for (int j0 = 0; j0 < grows; j0 += WB_ROWS) {
+                    const int nj = min(WB_ROWS, grows - j0);
+                    __syncthreads();
+                    if (rs < nj) {
+                        const int qrow = gs + j0 + rs;
+                        const size_t g = (size_t)qrow * C + head * D + c0;
+                        float r[DL], gg[DL], o[DL];
+                        load_row<DL>(r, p.q + g);
+                        load_row<DL>(gg, p.dout + g);
+                        load_row<DL>(o, p.out + g);
+                        float Dq = 0.f;
+#pragma unroll
+                        for (int d = 0; d < DL; d++) { s_a[rs * D + c0 + d] = r[d]; s_b[rs * D + c0 + d] = gg[d]; Dq = fmaf(gg[d], o[d], Dq); }
+                        Dq = quad_sum(Dq, qmask);
+                        if (c == 0) { s_c[rs * 2] = __ldg(p.lse + (size_t)qrow * p.h + head); s_c[rs * 2 + 1] = Dq; }
+                    }
+                    __syncthreads();
+                    if (!live) continue;
+                    // the queries of my window inside this chunk; pair (i, me) sits at sq + i_local * nw + il
+                    const int jb = max(ws - (gs + j0), 0), je = min(ws + nw - (gs + j0), nj);
+                    const int *rel = REL ? p.rel + (sq + (long long)(gs + j0 - ws) * nw + il) * 3 : nullptr;
+                    for (int j = jb; j < je; j++) {
+                        const float *qi = s_a + j * D + c0, *gi = s_b + j * D + c0;
+                        float s = 0.f, dp = 0.f;
+                        float tk[DL];
+                        int r0 = 0, r1 = 0, r2 = 0;
+                        if (REL) {
+                            const int *rp = rel + (long long)j * nw * 3;
+                            r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+                            float tq[DL], tv[DL];
+                            table_sum<DL>(tq, s_tq + c0, r0, r1, r2, D);
+                            table_sum<DL>(tk, s_tk + c0, r0, r1, r2, D);
+                            table_sum<DL>(tv, s_tv + c0, r0, r1, r2, D);
+#pragma unroll
+                            for (int d = 0; d < DL; d++) {
+                                s = fmaf(qi[d], kk[d] + tq[d], fmaf(kk[d], tk[d], s));
+                                dp = fmaf(gi[d], vv[d] + tv[d], dp);
+                            }
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < DL; d++) { s = fmaf(qi[d], kk[d], s); dp = fmaf(gi[d], vv[d], dp); }
+                        }
+                        s = quad_sum(s, qmask);
+                        dp = quad_sum(dp, qmask);
+                        const float pj = __expf(s - s_c[j * 2]);
+                        const float ds = pj * (dp - s_c[j * 2 + 1]);
+#pragma unroll
+                        for (int d = 0; d < DL; d++) {
+                            dk[d] = fmaf(ds, REL ? qi[d] + tk[d] : qi[d], dk[d]);
+                            dv[d] = fmaf(pj, gi[d], dv[d]);
+                        }
+                        if (REL && c < 3) s_h0[((c == 0 ? r0 : c == 1 ? r1 : r2) * 3 + c) * WB_ROWS + rs] += ds;
+                    }
+                }
+                if (live) {
+                    store_row<DL>(p.dk + (size_t)row * C + head * D + c0, dk);
+                    store_row<DL>(p.dv + (size_t)row * C + head * D + c0, dv);
+                }
+                if (REL) {
+                    __syncthreads();
+                    fold(s_h0, s_r0, n_rows, 1);   // dTk += Hds x k
+                }
             }
         }
-        // ---------------- pass B: columns (keys) ----------------
-        for (int j0 = 0; j0 < nw; j0 += WA_THREADS) {
-            const int j = j0 + tid;
-            const bool live = j < nw;
-            float kk[D], vv[D], dk[D], dv[D];
-#pragma unroll
-            for (int d = 0; d < D; d++) { dk[d] = 0.f; dv[d] = 0.f; }
-            if (live) {
-                load_row<D>(kk, p.k + (size_t)(start + j) * C + head * D);
-                load_row<D>(vv, p.v + (size_t)(start + j) * C + head * D);
-                if (REL) {
-#pragma unroll
-                    for (int d = 0; d < D; d++) s_r0[tid * D + d] = kk[d];
-                }
-            }
-            for (int i0 = 0; i0 < nw; i0 += WA_CHUNK) {
-                const int ni = min(WA_CHUNK, nw - i0);
-                __syncthreads();
-                if (tid < ni) {
-                    const size_t row = (size_t)(start + i0 + tid) * C + head * D;
-                    float r[D], g[D], o[D];
-                    load_row<D>(r, p.q + row);
-                    load_row<D>(g, p.dout + row);
-                    load_row<D>(o, p.out + row);
-                    float Di = 0.f;
-#pragma unroll
-                    for (int d = 0; d < D; d++) { s_a[tid * D + d] = r[d]; s_b[tid * D + d] = g[d]; Di = fmaf(g[d], o[d], Di); }
-                    s_c[tid * 2] = __ldg(p.lse + (size_t)(start + i0 + tid) * p.h + head);
-                    s_c[tid * 2 + 1] = Di;
-                }
-                __syncthreads();
-                if (!live) continue;
-                for (int i = 0; i < ni; i++) {
-                    const float *qi = s_a + i * D, *gi = s_b + i * D;
-                    float s = 0.f, dp = 0.f;
-                    float tk[D];
-                    int r0 = 0, r1 = 0, r2 = 0;
-                    if (REL) {
-                        const int *rel = p.rel + (sq + (long long)(i0 + i) * nw + j) * 3;
-                        r0 = __ldg(rel); r1 = __ldg(rel + 1); r2 = __ldg(rel + 2);
-                        float tq[D], tv[D];
-                        table_sum<D>(tq, s_tq, r0, r1, r2);
-                        table_sum<D>(tk, s_tk, r0, r1, r2);
-                        table_sum<D>(tv, s_tv, r0, r1, r2);
-#pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            s = fmaf(qi[d], kk[d] + tq[d], fmaf(kk[d], tk[d], s));
-                            dp = fmaf(gi[d], vv[d] + tv[d], dp);
-                        }
-                    } else {
-#pragma unroll
-                        for (int d = 0; d < D; d++) { s = fmaf(qi[d], kk[d], s); dp = fmaf(gi[d], vv[d], dp); }
-                    }
-                    const float pj = __expf(s - s_c[i * 2]);
-                    const float ds = pj * (dp - s_c[i * 2 + 1]);
-#pragma unroll
-                    for (int d = 0; d < D; d++) {
-                        dk[d] = fmaf(ds, REL ? qi[d] + tk[d] : qi[d], dk[d]);
-                        dv[d] = fmaf(pj, gi[d], dv[d]);
-                    }
-                    if (REL) {
-                        s_h0[(r0 * 3 + 0) * WA_THREADS + tid] += ds;
-                        s_h0[(r1 * 3 + 1) * WA_THREADS + tid] += ds;
-                        s_h0[(r2 * 3 + 2) * WA_THREADS + tid] += ds;
-                    }
-                }
-            }
-            if (live) {
-                float *ok = p.dk + (size_t)(start + j) * C + head * D, *ov = p.dv + (size_t)(start + j) * C + head * D;
-#pragma unroll
-                for (int d = 0; d < D; d += 4) {
-                    *reinterpret_cast<float4 *>(ok + d) = make_float4(dk[d], dk[d + 1], dk[d + 2], dk[d + 3]);
-                    *reinterpret_cast<float4 *>(ov + d) = make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]);
-                }
-            }
-            if (REL) {
-                const int n_live = min(WA_THREADS, nw - j0);
-                __syncthreads();
-                fold(s_h0, s_r0, n_live, 1);   // dTk += Hds x k
-                __syncthreads();
-            }
-        }
+        w0 = w1;
     }
     if (REL && p.part_smem) {
-        for (int e = tid; e < TS; e += WA_THREADS) {
+        __syncthreads();
+        for (int e = tid; e < TS; e += WB_THREADS) {
             const size_t g = ((size_t)(e / D) * p.h + head) * D + e % D;
             part[g] = s_part[e]; part[slice + g] = s_part[TS + e]; part[2 * slice + g] = s_part[2 * TS + e];
         }
@@ -412,6 +455,12 @@ int grid_x_bwd(int n_windows, int h) {
     return g < n_windows ? g : n_windows;
 }
 
+// table-free backward: ~17 KB of shared memory, 256 threads: 6 blocks per SM
+int grid_x_bwd_plain(int n_windows, int h) {
+    int g = (U2_NUM_SMS * 6 + h - 1) / h;
+    return g < n_windows ? g : n_windows;
+}
+
 int grid_x(int n_windows, int h) {
     int g = (U2_NUM_SMS * 16 + h - 1) / h;  // ~16 resident 64-thread blocks per SM over all heads
     return g < n_windows ? g : n_windows;
@@ -442,15 +491,14 @@ static int wa_launch_fwd(const WaParams &p, cudaStream_t st) {
 
 template <int D, bool REL>
 static int wa_launch_bwd(const WaParams &p, cudaStream_t st) {
-    size_t smem = (size_t)(2 * WA_CHUNK * D + 2 * WA_CHUNK + 2 * WA_THREADS * D +
-                           (REL ? 3 * p.L * 3 * D + 2 * p.L * 3 * WA_THREADS : 0)) * sizeof(float);
+    size_t smem = (size_t)(4 * WB_ROWS * D + 2 * WB_ROWS + (REL ? 3 * p.L * 3 * D + 2 * p.L * 3 * WB_ROWS : 0)) * sizeof(float);
     WaParams q = p;
     const size_t part_bytes = REL ? (size_t)3 * p.L * 3 * D * sizeof(float) : 0;
     q.part_smem = REL && smem + part_bytes <= 200 * 1024;   // else the folds add straight into the block's global slice
     if (q.part_smem) smem += part_bytes;
     U2_CUDA_OK(cudaFuncSetAttribute(window_attn_bwd_kernel<D, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int gx = REL ? grid_x_bwd(p.n_windows, p.h) : grid_x(p.n_windows, p.h);
-    window_attn_bwd_kernel<D, REL><<<dim3(gx, p.h), WA_THREADS, smem, st>>>(q);
+    const int gx = REL ? grid_x_bwd(p.n_windows, p.h) : grid_x_bwd_plain(p.n_windows, p.h);
+    window_attn_bwd_kernel<D, REL><<<dim3(gx, p.h), WB_THREADS, smem, st>>>(q);
     U2_LAUNCH_OK();
     if (REL) {
         const size_t tab = (size_t)p.L * 3 * p.h * D;
