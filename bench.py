@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-fused-sgd", action="store_true", help="torch's default (foreach) SGD instead of fused=True")
     ap.add_argument("--no-residual-fusion", action="store_true", help="ResidualBlock tail as separate add / ReLU passes")
     ap.add_argument("--no-conv-bn", action="store_true", help="BatchNorm as its own node after each conv (A/B of the conv+BN fusion)")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="coordinate work (voxel keys, kernel maps, tile sorts) of each batch inside its own step instead of on the prefetch stream under the previous step's backward")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu launch lists): no allocator pre-pass, no e2e region, no CPU baseline")
     return ap.parse_args()
@@ -288,10 +290,9 @@ def run_ours(args, w):
     pool = make_pool(args, w, rank, args.pool)
     n_params = sum(p.numel() for p in net.parameters())
 
-    def step(c, f, t):
-        x = ts.SparseTensor(f, c)
+    def step(x):
         out = net({"lidar": x})["x_vox"]
-        loss = torch.nn.functional.cross_entropy(out, t)
+        loss = torch.nn.functional.cross_entropy(out, x.targets)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -303,6 +304,7 @@ def run_ours(args, w):
         torch.cuda.synchronize()
 
     host_ms = {"last": 0.0}
+    prefetch = not args.no_prefetch
 
     def timed(n_steps, resident):
         """n_steps steps; resident=True: inputs already in HBM; False: pinned host -> device inside the
@@ -313,12 +315,44 @@ def run_ours(args, w):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t_host0 = time.perf_counter()
+        def load(i):
+            """Batch i as the model's input: device-resident tensors, or pinned host -> device copies on the current stream."""
+            c, f, t = dev_pool[i % len(pool)] if resident else (a.to(dev, non_blocking=True) for a in pool[i % len(pool)])
+            x = ts.SparseTensor(f, c)
+            x.targets = t
+            return x
+
+        def begin(i):
+            # coordinate-only work (and the H2D copies) of batch i on the prefetch stream, phase A: queued before step i - 1,
+            # it runs as soon as step i - 2 is off the GPU; all of it is inside the timed region, once per step
+            return fam.prepare_scan_begin(lambda: load(i), w["voxel_size"], w["voxel_size"])
+
+        steplog = [] if os.environ.get("U2_BENCH_STEPLOG") else None
+        prep = fam.prepare_scan_finish(begin(0)) if prefetch else None
         for i in range(n_steps):
-            if resident:
-                loss = step(*dev_pool[i % len(pool)])
+            t0 = time.perf_counter()
+            if prefetch:
+                x = prep.x
+                nxt = begin(i + 1) if i + 1 < n_steps else None
             else:
-                c, f, t = (a.to(dev, non_blocking=True) for a in pool[i % len(pool)])
-                loss = step(c, f, t)
+                x = load(i)
+            t1 = time.perf_counter()
+            loss = step(x)
+            t2 = time.perf_counter()
+            if prefetch and nxt is not None:
+                prep = fam.prepare_scan_finish(nxt)   # phase B: row counts are in pinned memory by now; queue the map builders
+            if steplog is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                ms_ = torch.cuda.memory_stats()
+                try:
+                    hs_ = torch.cuda.host_memory_stats().get("num_host_alloc", -1)
+                except Exception:
+                    hs_ = -1
+                steplog.append((ev, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3,
+                                ms_.get("num_device_alloc", -1), ms_.get("num_device_free", -1), hs_,
+                                ms_.get("reserved_bytes.all.current", 0) >> 20))
+            if not resident:
                 # D2H of the step's result, every step, asynchronously into pinned memory (read after the
                 # region's closing synchronize — a training loop logs the loss without stalling the queue)
                 loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
@@ -327,6 +361,13 @@ def run_ours(args, w):
         barrier()
         if not resident:
             assert bool(torch.isfinite(loss_host).all()), "non-finite loss"
+        if steplog:
+            prev = e0
+            rows = []
+            for ev, a, b, c, na, nf, nh, rs in steplog:
+                rows.append(f"gpu {prev.elapsed_time(ev):6.1f} | host begin {a:5.1f} step {b:5.1f} finish {c:5.1f} | cudaMalloc {na} cudaFree {nf} hostAlloc {nh} reserved {rs} MB")
+                prev = ev
+            print(f"[steplog resident={resident}]\n  " + "\n  ".join(rows), file=sys.stderr, flush=True)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -337,6 +378,8 @@ def run_ours(args, w):
     # then the W warm-up steps proper
     if not args.quick:
         timed(len(pool), True)
+        if prefetch:
+            timed(len(pool), True)   # the prefetch stream has its own allocator pool, filled one batch ahead of the main one
     timed(args.warmup, True)
     sampler = ClockSampler(local)
     timer = ConvTimer()
@@ -358,6 +401,17 @@ def run_ours(args, w):
     ops.conv_timer = None
     ops.set_overlap_rows(saved_overlap)
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("U2_BENCH_HOSTPROF") and rank == 0:
+        # where the host spends its time queueing a step (untimed extra pass; cProfile slows the host down ~2x)
+        import cProfile, pstats, io
+        pr = cProfile.Profile()
+        pr.enable()
+        timed(args.steps, True)
+        pr.disable()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+        with open(os.environ["U2_BENCH_HOSTPROF"], "w") as fh:
+            fh.write(buf.getvalue())
     if args.quick:
         ms_e2e = ms
     else:
@@ -441,6 +495,7 @@ def run_ours(args, w):
                            "fused_residual": not (args.no_fusion or args.no_conv_bn or args.no_residual_fusion),
                            "optimizer_impl": "torch fused" if not args.no_fused_sgd else "torch foreach",
                            "dgrad_wgrad_overlap_rows": ops._state["overlap_rows"],
+                           "coord_prefetch": prefetch,
                            "l2": "activations (>1 GB/step) exceed the 126 MB L2; a different scan batch every step"},
                 "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},

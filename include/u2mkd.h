@@ -185,6 +185,18 @@ int u2_conv_fwd_perm(const float *X, int64_t n_src, int32_t Cs, const float *W, 
  * (u2_conv_scratch_bytes(., K, Cin, Cout, math) bytes), blob_dgrad for W[k]^T (.., Cout, Cin, ..); either may be NULL. */
 int u2_conv_pretile(const float *W, int32_t K, int32_t Cin, int32_t Cout, int32_t math, void *blob_fwd, void *blob_dgrad,
                     u2_stream_t stream);
+/* The same for every conv parameter of a model in ONE launch per optimizer step (the reference re-reads `kernel` in every
+ * conv launch, [TS backend/convolution/convolution_cuda.cu]; per-layer u2_conv_pretile calls were 2 small launches per layer).
+ * u2_conv_pretile_plan writes a job table for n_jobs (parameter, direction) pairs into the HOST buffer plan_host
+ * (u2_conv_pretile_plan_bytes(n_jobs) bytes): job i re-tiles the fp32 tensor at device address W[i] — [K, Cs, Cd], or
+ * [K, Cd, Cs] when w_transposed[i] (the input-gradient direction of a [K, Cin, Cout] parameter: Cs = Cout, Cd = Cin) — into
+ * the blob at device address blob[i].  bf16 blobs only.  The caller copies the table to device memory once and calls
+ * u2_conv_pretile_run(plan_dev, n_jobs, *n_blocks) whenever the parameters have changed.                              */
+size_t u2_conv_pretile_plan_bytes(int32_t n_jobs);
+int u2_conv_pretile_plan(int32_t n_jobs, const uint64_t *W, const uint64_t *blob, const int32_t *K, const int32_t *Cs,
+                         const int32_t *Cd, const int32_t *w_transposed, int32_t math, void *plan_host, size_t plan_bytes,
+                         int64_t *n_blocks);
+int u2_conv_pretile_run(const void *plan_dev, int32_t n_jobs, int64_t n_blocks, u2_stream_t stream);
 
 /* ---- BatchNorm (+ fused ReLU) over feature matrices fp32 [n, C], training mode: what the reference runs as
  * torch BatchNorm1d / SyncBatchNorm + ReLU on SparseTensor.F after every conv

@@ -205,13 +205,85 @@ def test_prebuilt_kernel_maps_do_not_change_the_model(cuda_lib):
     assert len(ops._plan) >= 9, ops._plan.keys()   # 5 strides of k3 maps + 4 k2s2 maps
     assert any("sortF" in v or "flat" in v or not v for v in ops._plan.values())
     built = []
-    orig = F.prebuild_maps
-    F.prebuild_maps = lambda x: built.append(orig(x))
+    orig = ops.prebuild_maps
+
+    def counting(x):
+        built.append(orig(x))
+        return built[-1]
+    ops.prebuild_maps = counting
     try:
         pre = run()
     finally:
-        F.prebuild_maps = orig
+        ops.prebuild_maps = orig
     assert built == [len(ops._plan)], (built, len(ops._plan))   # every map of the second pass was built up front
     # (scatter-mean and the FFMA wgrad accumulate with fp32 atomics: two passes agree to rounding, not bitwise)
     assert float((lazy[0] - pre[0]).abs().max()) <= 1e-5 * float(lazy[0].abs().max())
     assert float((lazy[1] - pre[1]).abs().max()) <= 1e-4 * float(lazy[1].abs().max())
+
+
+def test_prefetched_coordinates_do_not_change_the_model(cuda_lib):
+    """prepare_scan: voxel keys, unique and every kernel map of a batch computed on the prefetch stream (under the previous
+    batch's backward in a training loop) — the step then holds no host synchronisation.  Same index tensors bit for bit,
+    logits / gradients as in the in-place pass, over several alternating batches (memory handed between the two streams)."""
+    from u2mkd_b200 import models, ops, scans
+    import u2mkd_b200.torchsparse as ts
+    ops.set_math("fp32")
+    ops.set_prebuild(False)
+    ops.set_prebuild(True)
+    fam = models.product()
+    batches = []
+    for seed in (3, 4, 5):
+        coords, feats = scans.make_batch([seed], "nusc", 1, 0.2)
+        batches.append((torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()))
+    torch.manual_seed(0)
+    net = fam.SPVCNN(cr=0.5, pres=0.2, vres=0.2, num_classes=17).cuda()
+    net.dropout = torch.nn.Identity()
+
+    def run(x):
+        net.zero_grad()
+        out = net({"lidar": x})["x_vox"]
+        out.square().mean().backward()
+        return out.detach().clone(), net.stem[0].kernel.grad.detach().clone()
+
+    plain = [run(ts.SparseTensor(f, c)) for c, f in batches]          # also records the map plan
+    # scatter-mean and the FFMA wgrad accumulate with fp32 atomics: identical passes agree to rounding, not bitwise, and 49
+    # BatchNorm layers at random init amplify that rounding in the gradients (module docstring): measure it
+    noise = [(0.0, 0.0)] * len(batches)
+    for _ in range(3):
+        again = [run(ts.SparseTensor(f, c)) for c, f in batches]
+        noise = [tuple(max(nz, float((a - b).abs().max())) for nz, a, b in zip(n3, p, q)) for n3, p, q in zip(noise, plain, again)]
+    pre = []
+    n = 2 * len(batches)
+    prep = fam.prepare_scan(ts.SparseTensor(batches[0][1], batches[0][0]), 0.2, 0.2)
+    for i in range(n):
+        nxt = None
+        if i + 1 < n:                                                 # the training-loop pattern: phase A of the next batch,
+            c, f = batches[(i + 1) % len(batches)]
+            nxt = fam.prepare_scan_begin(lambda c=c, f=f: ts.SparseTensor(f, c), 0.2, 0.2)
+        assert len(prep.kmaps) == len(ops._plan) and prep.idx_query.shape[0] == prep.x.C.shape[0]
+        n_maps = len(prep.kmaps)
+        pre.append(run(prep.x))                                    # the current step,
+        assert len(prep.kmaps) == n_maps                           # (whose forward pass built nothing itself)
+        if nxt is not None:
+            prep = fam.prepare_scan_finish(nxt)                       # phase B of the next batch
+    torch.cuda.synchronize()
+    for i, got in enumerate(pre):
+        want = plain[i % len(batches)]
+        nz = noise[i % len(batches)]
+        assert got[0].shape == want[0].shape
+        assert float((want[0] - got[0]).abs().max()) <= max(1e-5 * float(want[0].abs().max()), 10 * nz[0]), i
+        assert float((want[1] - got[1]).abs().max()) <= max(1e-4 * float(want[1].abs().max()), 10 * nz[1]), (i, nz)
+    # index tensors of the prefetch path against the in-place operators
+    c, f = batches[0]
+    zc = c.float()
+    fl = torch.floor(torch.cat([(zc[:, :3] * 0.2) / 0.2, zc[:, -1].view(-1, 1)], 1)).int()
+    iq, cnt, vox = ops.unique_voxelize(fl)
+    p0 = fam.prepare_scan(ts.SparseTensor(f, c), 0.2, 0.2)
+    torch.cuda.current_stream().wait_event(p0.done)
+    assert torch.equal(p0.idx_query, iq) and torch.equal(p0.counts, cnt) and torch.equal(p0.coords, vox)
+    # the coarse coordinate sets computed straight from the points = the chained spdownsample results
+    from u2mkd_b200.torchsparse.nn import functional as F
+    cur = vox
+    for s_ in (2, 4, 8, 16):
+        cur = F.spdownsample(cur, 2, 2, s_ // 2)
+        assert torch.equal(p0.cmaps[(s_, s_, s_)], cur), s_

@@ -591,3 +591,53 @@ def test_wgrad_dense_hint_is_withdrawn_for_duplicate_coordinates(tc, oracle):
     dk, flag = list(x.kmaps.values())[0].dense_hint()
     assert dk == 13 and int(flag) == 0
     assert rel_err(conv_g.kernel.grad, conv_o.kernel.grad) < 2e-2
+
+
+@pytest.mark.gpu
+def test_one_launch_weight_retiling_matches_per_layer_blobs():
+    """u2_conv_pretile_plan / _run (all parameters of a model in one launch) writes the same bytes as per-layer u2_conv_pretile,
+    and ops.weight_blobs re-tiles when — and only when — a parameter's version moves."""
+    import ctypes
+    from u2mkd_b200 import ops
+    from u2mkd_b200._lib import lib
+    l = lib()
+    torch.manual_seed(3)
+    shapes = [(27, 64, 64), (8, 64, 128), (1, 256, 192), (27, 192, 256), (27, 128, 128)]
+    ws = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = []
+    for w in ws:
+        K, cin, cout = w.shape
+        nb = K * cin * cout * 2
+        b = torch.zeros(2 * nb, dtype=torch.uint8, device="cuda")
+        assert l.u2_conv_pretile(w.data_ptr(), K, cin, cout, ops.MATH_BF16, b.data_ptr(), b.data_ptr() + nb, None) == 0
+        ref.append(b)
+    arena = ops._WeightBlobs()
+    got = [arena.get(w) for w in ws]                      # registration: per-layer launches
+    for (bf, bd), r in zip(got, ref):
+        assert torch.equal(torch.cat([bf, bd]), r)
+    n0 = ops.stats["launches"]
+    assert all(arena.get(w)[0].data_ptr() == g[0].data_ptr() for w, g in zip(ws, got))
+    assert ops.stats["launches"] == n0                   # nothing changed: no launch
+    with torch.no_grad():
+        for w in ws:
+            w.mul_(0.5)
+    ref2 = []
+    for w in ws:
+        K, cin, cout = w.shape
+        nb = K * cin * cout * 2
+        b = torch.zeros(2 * nb, dtype=torch.uint8, device="cuda")
+        assert l.u2_conv_pretile(w.data_ptr(), K, cin, cout, ops.MATH_BF16, b.data_ptr(), b.data_ptr() + nb, None) == 0
+        ref2.append(b)
+    n0 = ops.stats["launches"]
+    got2 = [arena.get(w) for w in ws]
+    assert ops.stats["launches"] == n0 + 1               # ONE launch for all ten blobs
+    for (bf, bd), r in zip(got2, ref2):
+        assert torch.equal(torch.cat([bf, bd]), r)
+    # a bad job is refused on the host
+    nblk = ctypes.c_int64(0)
+    import numpy as np
+    one = np.array([ws[0].data_ptr()], np.uint64)
+    k = np.array([27], np.int32); cs = np.array([7], np.int32); cd = np.array([64], np.int32); t = np.array([0], np.int32)
+    host = np.zeros(l.u2_conv_pretile_plan_bytes(1), np.uint8)
+    assert l.u2_conv_pretile_plan(1, one.ctypes.data, one.ctypes.data, k.ctypes.data, cs.ctypes.data, cd.ctypes.data, t.ctypes.data,
+                                  ops.MATH_BF16, host.ctypes.data, host.nbytes, ctypes.addressof(nblk)) != 0

@@ -91,6 +91,9 @@ _SIGNATURES = {
     "u2_syncbn_max_world": (_i32, []),
     "u2_syncbn_exchange": (ctypes.c_int, [_p, _i32, _p, _i32, _i32, ctypes.c_uint64, _p]),
     "u2_conv_pretile": (ctypes.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "u2_conv_pretile_plan_bytes": (ctypes.c_size_t, [_i32]),
+    "u2_conv_pretile_plan": (ctypes.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i32, _p, _sz, _p]),
+    "u2_conv_pretile_run": (ctypes.c_int, [_p, _i32, _i64, _p]),
     "u2_conv_tc_shape_supported": (ctypes.c_int, [_i32, _i32, _i32, _i32]),
     "u2_conv_tile_stats_parts": (ctypes.c_size_t, [_i64]),
     "u2_conv_fwd_stats": (ctypes.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _sz, _p, _sz, _p]),

@@ -14,6 +14,11 @@ int u2_conv_tc_supported(int32_t Cs, int32_t Cd, int32_t K, int32_t math);
 int u2_conv_fwd_tc(const void *X, int64_t n_src, int32_t Cs, const float *W, int32_t w_transposed, const int32_t *table,
                    const int32_t *perm, int64_t ld, int64_t n_dst, int32_t K, int32_t Cd, float *Y, int32_t math,
                    void *scratch, size_t scratch_bytes, float *tile_stats, const float *Yadd, cudaStream_t st);
+size_t u2_conv_pretile_plan_bytes_tc(int32_t n_jobs);
+int u2_conv_pretile_plan_tc(int32_t n_jobs, const uint64_t *W, const uint64_t *blob, const int32_t *K, const int32_t *Cs,
+                            const int32_t *Cd, const int32_t *w_transposed, int32_t math, void *plan_host, size_t plan_bytes,
+                            int64_t *n_blocks);
+int u2_conv_pretile_run_tc(const void *plan_dev, int32_t n_jobs, int64_t n_blocks, cudaStream_t st);
 int u2_conv_pretile_tc(const float *W, int32_t w_transposed, int32_t K, int32_t Cs, int32_t Cd, int32_t math, void *blob,
                        cudaStream_t st);
 int u2_cast_bf16_impl(const float *x, int64_t n, void *y, cudaStream_t st);
@@ -175,6 +180,37 @@ extern "C" int u2_conv_pretile(const float *W, int32_t K, int32_t Cin, int32_t C
 #else
     (void)W; (void)K; (void)Cin; (void)Cout; (void)math; (void)blob_fwd; (void)blob_dgrad; (void)stream;
     u2_set_error("u2_conv_pretile: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+extern "C" size_t u2_conv_pretile_plan_bytes(int32_t n_jobs) {
+#ifdef U2_WITH_TC
+    return u2_conv_pretile_plan_bytes_tc(n_jobs);
+#else
+    (void)n_jobs;
+    return 0;
+#endif
+}
+
+extern "C" int u2_conv_pretile_plan(int32_t n_jobs, const uint64_t *W, const uint64_t *blob, const int32_t *K, const int32_t *Cs,
+                                    const int32_t *Cd, const int32_t *w_transposed, int32_t math, void *plan_host,
+                                    size_t plan_bytes, int64_t *n_blocks) {
+#ifdef U2_WITH_TC
+    return u2_conv_pretile_plan_tc(n_jobs, W, blob, K, Cs, Cd, w_transposed, math, plan_host, plan_bytes, n_blocks);
+#else
+    (void)n_jobs; (void)W; (void)blob; (void)K; (void)Cs; (void)Cd; (void)w_transposed; (void)math; (void)plan_host; (void)plan_bytes; (void)n_blocks;
+    u2_set_error("u2_conv_pretile_plan: built without the tcgen05 path");
+    return 1;
+#endif
+}
+
+extern "C" int u2_conv_pretile_run(const void *plan_dev, int32_t n_jobs, int64_t n_blocks, u2_stream_t stream) {
+#ifdef U2_WITH_TC
+    return u2_conv_pretile_run_tc(plan_dev, n_jobs, n_blocks, (cudaStream_t)stream);
+#else
+    (void)plan_dev; (void)n_jobs; (void)n_blocks; (void)stream;
+    u2_set_error("u2_conv_pretile_run: built without the tcgen05 path");
     return 1;
 #endif
 }

@@ -1246,10 +1246,9 @@ __device__ __forceinline__ unsigned int pack_bf16x2(float lo, float hi) {
 
 // fp32 weights -> bf16 blobs [k][cc][nt][chunk][n][8] (K-major UMMA layout, 16-byte chunk = 8 channels)
 template <bool WT>
-__global__ void __launch_bounds__(256) pretile_weights_bf16_kernel(const float *__restrict__ W, uint4 *__restrict__ out, int K,
-                                                                   int Cs, int Cd, int KC, int NT) {
+__device__ __forceinline__ void pretile_bf16_piece(const float *__restrict__ W, uint4 *__restrict__ out, int K, int Cs, int Cd, int KC,
+                                                   int NT, int64_t t) {
     const int64_t total = (int64_t)K * Cs * Cd / 8;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int chunks = KC / 8, n_cc = Cs / KC, n_nt = Cd / NT;
     int64_t r = t;
@@ -1264,6 +1263,32 @@ __global__ void __launch_bounds__(256) pretile_weights_bf16_kernel(const float *
     for (int e = 0; e < 8; e++)
         v[e] = WT ? __ldg(W + ((int64_t)k * Cd + cd) * Cs + cs + e) : __ldg(W + ((int64_t)k * Cs + cs + e) * Cd + cd);
     out[t] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+template <bool WT>
+__global__ void __launch_bounds__(256) pretile_weights_bf16_kernel(const float *__restrict__ W, uint4 *__restrict__ out, int K,
+                                                                   int Cs, int Cd, int KC, int NT) {
+    pretile_bf16_piece<WT>(W, out, K, Cs, Cd, KC, NT, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// every (parameter, direction) of a model in ONE launch: the job table says which blocks belong to which re-tiling
+struct PretileJob {
+    const float *W;
+    uint4 *out;
+    int64_t block_start;  // first thread block of this job
+    int K, Cs, Cd, KC, NT, WT;
+};
+
+__global__ void __launch_bounds__(256) pretile_multi_bf16_kernel(const PretileJob *__restrict__ jobs, int n_jobs) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].block_start <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PretileJob j = jobs[lo];
+    const int64_t t = ((int64_t)blockIdx.x - j.block_start) * blockDim.x + threadIdx.x;
+    if (j.WT) pretile_bf16_piece<true>(j.W, j.out, j.K, j.Cs, j.Cd, j.KC, j.NT, t);
+    else pretile_bf16_piece<false>(j.W, j.out, j.K, j.Cs, j.Cd, j.KC, j.NT, t);
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4 *__restrict__ x, int64_t n8, uint4 *__restrict__ y) {
@@ -1434,6 +1459,42 @@ int u2_conv_pretile_tc(const float *W, int32_t w_transposed, int32_t K, int32_t 
         else
             pretile_weights_kernel<false><<<(unsigned)u2_ceil_div(total4, 256), 256, 0, st>>>(W, (float4 *)blob, K, Cs, Cd, KC, NT);
     }
+    U2_LAUNCH_OK();
+    return 0;
+}
+
+size_t u2_conv_pretile_plan_bytes_tc(int32_t n_jobs) { return (size_t)(n_jobs > 0 ? n_jobs : 0) * sizeof(PretileJob); }
+
+// host side of the one-launch re-tiling: job table for n (parameter, direction) pairs, in the caller's (host) buffer
+int u2_conv_pretile_plan_tc(int32_t n_jobs, const uint64_t *W, const uint64_t *blob, const int32_t *K, const int32_t *Cs,
+                            const int32_t *Cd, const int32_t *w_transposed, int32_t math, void *plan_host, size_t plan_bytes,
+                            int64_t *n_blocks) {
+    U2_CHECK_ARG(math == U2_MATH_BF16, "u2_conv_pretile_plan: bf16 blobs only (math %d)", math);
+    U2_CHECK_ARG(n_jobs >= 0 && n_blocks && (n_jobs == 0 || (W && blob && K && Cs && Cd && w_transposed && plan_host)),
+                 "u2_conv_pretile_plan: null pointer");
+    U2_CHECK_ARG(plan_bytes >= u2_conv_pretile_plan_bytes_tc(n_jobs), "u2_conv_pretile_plan: plan buffer too small");
+    PretileJob *jobs = (PretileJob *)plan_host;
+    int64_t blocks = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const int ROWB = pick_rowb(Cs[i], 2), NT = pick_nt(Cd[i]);
+        U2_CHECK_ARG(ROWB && NT && K[i] > 0 && K[i] <= 32, "u2_conv_pretile_plan: job %d: unsupported shape Cs=%d Cd=%d K=%d", i, Cs[i],
+                     Cd[i], K[i]);
+        U2_CHECK_ARG(W[i] && blob[i] && ((W[i] | blob[i]) & 15) == 0, "u2_conv_pretile_plan: job %d: null or misaligned pointer", i);
+        jobs[i].W = (const float *)(uintptr_t)W[i];
+        jobs[i].out = (uint4 *)(uintptr_t)blob[i];
+        jobs[i].block_start = blocks;
+        jobs[i].K = K[i]; jobs[i].Cs = Cs[i]; jobs[i].Cd = Cd[i]; jobs[i].KC = ROWB / 2; jobs[i].NT = NT; jobs[i].WT = w_transposed[i] ? 1 : 0;
+        blocks += u2_ceil_div((int64_t)K[i] * Cs[i] * Cd[i] / 8, 256);
+    }
+    U2_CHECK_ARG(blocks < (int64_t)1 << 31, "u2_conv_pretile_plan: too many thread blocks");
+    *n_blocks = blocks;
+    return 0;
+}
+
+int u2_conv_pretile_run_tc(const void *plan_dev, int32_t n_jobs, int64_t n_blocks, cudaStream_t st) {
+    U2_CHECK_ARG(n_jobs >= 0 && n_blocks >= 0 && (n_jobs == 0 || plan_dev), "u2_conv_pretile_run: bad arguments");
+    if (n_jobs == 0 || n_blocks == 0) return 0;
+    pretile_multi_bf16_kernel<<<(unsigned)n_blocks, 256, 0, st>>>((const PretileJob *)plan_dev, n_jobs);
     U2_LAUNCH_OK();
     return 0;
 }

@@ -13,12 +13,21 @@ present on the GPU box where bench.py and the -m gpu tests run.
 """
 from __future__ import annotations
 
+import weakref
 from types import SimpleNamespace
 
 import torch
 from torch import nn
 
 CHANNELS = (32, 32, 64, 128, 256, 256, 128, 96, 96)
+
+
+class PreparedScan:
+    """What prepare_scan_begin / _finish know about a scan batch: x (the input SparseTensor), res, and after phase B
+    idx_query / counts / coords / cmaps / kmaps / done (event on the prefetch stream)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
 
 
 def build_family(ts) -> SimpleNamespace:
@@ -33,14 +42,59 @@ def build_family(ts) -> SimpleNamespace:
         """Voxel key of every point at stride s: (floor(xyz / s) * s, batch), int32 [N,4]."""
         return torch.cat([torch.floor(z.C[:, :3] / s).int() * s, z.C[:, -1].int().view(-1, 1)], 1)
 
+    def _voxel_keys(zc, init_res, after_res):
+        new_float_coord = torch.cat([(zc[:, :3] * init_res) / after_res, zc[:, -1].view(-1, 1)], 1)
+        return new_float_coord, torch.floor(new_float_coord)
+
+    def prepare_scan_begin(x_in, init_res, after_res):
+        """Product path only, phase A of the coordinate prefetch for the scan batch `x_in` (the SparseTensor that will be
+        passed as in_mod["lidar"], or a callable returning it — e.g. the host -> device copies): call it BEFORE queueing the
+        current step.  Launches voxel keys, unique and the coarse coordinate sets on the prefetch stream; no host wait."""
+        from . import ops
+
+        def work():
+            x = x_in() if callable(x_in) else x_in
+            _nfc, floored = _voxel_keys(x.C.float(), init_res, after_res)
+            return PreparedScan(x=x, src=x.C, res=(init_res, after_res), a=ops.coords_begin(floored.int()), done=None)
+
+        return ops.coord_prefetch.begin(work)
+
+    def prepare_scan_finish(prep):
+        """Phase B: call it AFTER queueing the current step.  Reads the row counts phase A left in pinned memory and queues
+        every kernel map / tile sort / pair list an earlier forward asked for.  prep.x is the batch to pass to the model (keep
+        `prep` alive until that forward pass has run); initial_voxelize picks the results up (same values as in place)."""
+        from . import ops
+
+        def work():
+            prep.idx_query, prep.counts, prep.coords, prep.cmaps, prep.kmaps = ops.coords_finish(prep.a, SparseTensor)
+            prep.a = None
+            return prep
+
+        _, prep.done = ops.coord_prefetch.finish(work)
+        # weak: prep holds x; a strong reference back would make a cycle that only the cyclic collector frees — device memory
+        # of old batches would be released late and at random (measured: the prefetch pool grew by 370 MB per step)
+        prep.x._u2_prep = weakref.ref(prep)
+        return prep
+
+    def prepare_scan(x_in, init_res, after_res):
+        """Both phases back to back (blocks until phase A's kernels have run)."""
+        return prepare_scan_finish(prepare_scan_begin(x_in, init_res, after_res))
+
     def initial_voxelize(z, init_res, after_res):
         """utils.py:15-35 — quantise, hash, unique, scatter-mean coords + features."""
-        new_float_coord = torch.cat([(z.C[:, :3] * init_res) / after_res, z.C[:, -1].view(-1, 1)], 1)
-        floored = torch.floor(new_float_coord)
+        new_float_coord, floored = _voxel_keys(z.C, init_res, after_res)
         fused = getattr(spf, "unique_voxelize", None)
-        if fused is not None and floored.is_cuda:
-            # product path: the five index operators below as one call (same voxel order, same idx_query / counts / coords)
-            idx_query, counts, coords = fused(floored.int())
+        prep = getattr(z, "_u2_prep", None)
+        cmaps = kmaps = None
+        if prep is not None and prep.done is not None and prep.res == (init_res, after_res) and floored.is_cuda:
+            # product path with prepare_scan_*(): the index part and the kernel maps were computed on the prefetch stream
+            torch.cuda.current_stream().wait_event(prep.done)
+            idx_query, counts, coords, cmaps, kmaps = prep.idx_query, prep.counts, prep.coords, prep.cmaps, prep.kmaps
+        elif fused is not None and floored.is_cuda:
+            # product path: the five index operators below as one call (same voxel order, same idx_query / counts / coords),
+            # the coarse coordinate sets next to it and ONE host wait for all row counts, then every planned kernel map
+            from . import ops
+            idx_query, counts, coords, cmaps, kmaps = ops.coords_finish(ops.coords_begin(floored.int()), SparseTensor)
         else:
             pc_hash = spf.sphash(floored.int())
             sparse_hash = torch.unique(pc_hash)
@@ -49,10 +103,12 @@ def build_family(ts) -> SimpleNamespace:
             coords = torch.round(spf.spvoxelize(floored, idx_query, counts)).int()
         feats = spf.spvoxelize(z.F, idx_query, counts)
         x = SparseTensor(feats, coords, 1)
+        if cmaps is not None:
+            x.cmaps, x.kmaps = cmaps, kmaps
         x.cmaps.setdefault(x.stride, x.coords)
         prebuild = getattr(spf, "prebuild_maps", None)
-        if prebuild is not None and coords.is_cuda:
-            prebuild(x)  # product path: the kernel maps of every layer now, all host synchronisations before the first conv
+        if prebuild is not None and coords.is_cuda and cmaps is None:
+            prebuild(x)  # (a torchsparse namespace with prebuild_maps but without unique_voxelize)
         z.additional_features["idx_query"][1] = idx_query
         z.additional_features["counts"][1] = counts
         z.C = new_float_coord
@@ -214,6 +270,10 @@ def build_family(ts) -> SimpleNamespace:
         def forward(self, in_mod):
             x = in_mod["lidar"]
             z = PointTensor(x.F, x.C.float())
+            prep = getattr(x, "_u2_prep", None)
+            prep = prep() if prep is not None else None
+            if prep is not None and prep.src is x.C:
+                z._u2_prep = prep   # prepare_scan() ran for this batch
             x0 = self.stem(initial_voxelize(z, self.pres, self.vres))
             z0 = voxel_to_point(x0, z, nearest=False)
 
@@ -240,7 +300,8 @@ def build_family(ts) -> SimpleNamespace:
             z3.F = z3.F + self.point_transforms[2](z2.F)
             return {"x_vox": self.classifier_vox(z3.F)}
 
-    return SimpleNamespace(initial_voxelize=initial_voxelize, point_to_voxel=point_to_voxel,
+    return SimpleNamespace(initial_voxelize=initial_voxelize, prepare_scan=prepare_scan, prepare_scan_begin=prepare_scan_begin,
+                           prepare_scan_finish=prepare_scan_finish, point_to_voxel=point_to_voxel,
                            voxel_to_point=voxel_to_point, fetch_idx=fetch_idx,
                            SparseSyncBatchNorm=SparseSyncBatchNorm,
                            BasicConvolutionBlock=BasicConvolutionBlock,

@@ -9,6 +9,7 @@ in oracle/ and is test infrastructure).
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -27,8 +28,12 @@ stats = {"launches": 0}
 conv_timer = None  # object with .record(kind, table, n_dst, K, c_src, c_dst, ev_start, ev_stop)
 
 
+_count_lock = threading.Lock()
+
+
 def _count(n: int = 1) -> None:
-    stats["launches"] += n
+    with _count_lock:   # the coordinate prefetch launches from a worker thread
+        stats["launches"] += n
 
 
 def set_math(mode: str) -> None:
@@ -86,7 +91,7 @@ def _ws(name: str, nbytes: int, device) -> torch.Tensor:
     stream: every user of one `name` launches on the same stream, so the next kernel that overwrites the buffer runs after
     the previous reader (forward: the caller's stream; autograd replays backward on that stream too).  Side-stream users
     pass their own name.  Saves ~350 torch.empty calls (1.5 ms of host time) per training step."""
-    key = (name, torch.device(device).index)
+    key = (name, torch.device(device).index, _st())  # per stream: the coordinate prefetch runs the map builders on its own
     t = _workspaces.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
@@ -203,6 +208,79 @@ def unique_voxelize(coords: torch.Tensor):
     _count(5)
     m = int(n_vox.item())
     return idx_query, counts[:m], vox[:m]
+
+
+def _unique_voxelize_launch(coords: torch.Tensor, n_dev: torch.Tensor):
+    """unique_voxelize without the host read of the voxel count (written to n_dev[0]); outputs sized for n voxels."""
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    dev = coords.device
+    idx_query = torch.empty(n, dtype=torch.int64, device=dev)
+    counts = torch.empty(n, dtype=torch.int, device=dev)
+    vox = torch.empty((n, 4), dtype=torch.int, device=dev)
+    scratch = _ws("uvox", lib().u2_unique_voxelize_scratch_bytes(n), dev)
+    check(lib().u2_unique_voxelize(coords.data_ptr(), n, idx_query.data_ptr(), counts.data_ptr(), vox.data_ptr(),
+                                   n_dev.data_ptr(), scratch.data_ptr(), scratch.numel(), _st()))
+    _count(5)
+    return idx_query, counts, vox
+
+
+def _downsample_launch(coords: torch.Tensor, sample_stride, n_dev: torch.Tensor) -> torch.Tensor:
+    """downsample_coords without the host read of the row count (written to n_dev[0]); output sized for n rows."""
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    sbytes = lib().u2_downsample_scratch_bytes(n)
+    scratch = _ws("downs", sbytes, coords.device)
+    out = torch.empty((n, 4), dtype=torch.int, device=coords.device)
+    check(lib().u2_downsample_coords(coords.data_ptr(), n, int(sample_stride[0]), int(sample_stride[1]),
+                                     int(sample_stride[2]), out.data_ptr(), n_dev.data_ptr(), scratch.data_ptr(), sbytes,
+                                     _st()))
+    _count(4)
+    return out
+
+
+def planned_strides():
+    """Tensor strides of the coordinate sets the prebuild plan's strided convs produce, ascending."""
+    out = set()
+    for (in_stride, ks, stride, _dil) in _plan:
+        # (the stride in {1, kernel_size} case of spdownsample, the only one U2MKD's models use; others stay lazy)
+        if any(v > 1 for v in stride) and all(stride[a] in (1, ks[a]) for a in range(3)):
+            out.add(tuple(in_stride[a] * stride[a] for a in range(3)))
+    return sorted(out)
+
+
+def coords_begin(floored: torch.Tensor):
+    """Phase A of a scan batch's coordinate pipeline, no host synchronisation: voxel keys -> unique (stride-1 voxels in the
+    reference's order) and, straight from the same point rows, the coordinate set of every coarser stride the prebuild
+    plan knows (unique(floor(c / s) * s) of the points = of the voxels = the chained spdownsample results); all row counts
+    go to one pinned host buffer with one asynchronous copy.  `floored`: int32 [N,4] point coordinates."""
+    _need_cuda(floored)
+    strides = planned_strides() if _state.get("prebuild", True) else []
+    n_dev = torch.empty(1 + len(strides), dtype=torch.int64, device=floored.device)
+    idx_query, counts, vox = _unique_voxelize_launch(floored, n_dev[0:1])
+    coarse = [_downsample_launch(floored, s, n_dev[i + 1:i + 2]) for i, s in enumerate(strides)]
+    n_host = torch.empty(n_dev.shape[0], dtype=torch.int64, pin_memory=True)
+    n_host.copy_(n_dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return {"idx_query": idx_query, "counts": counts, "vox": vox, "strides": strides, "coarse": coarse, "n_host": n_host,
+            "n_dev": n_dev, "ready": ev}
+
+
+def coords_finish(h, SparseTensor):
+    """Phase B: read the row counts (ONE wait, for work queued in phase A), slice the coordinate sets and build every
+    planned kernel map / tile sort / pair list on them.  Returns (idx_query, counts, coords, cmaps, kmaps)."""
+    h["ready"].synchronize()
+    ns = [int(v) for v in h["n_host"].tolist()]
+    if min(ns) < 0:
+        raise RuntimeError("downsample_coords: coordinates outside [0, 2^18) or batch outside [0, 1024)")
+    coords = h["vox"][:ns[0]]
+    holder = SparseTensor(coords.new_zeros((0, 1), dtype=torch.float32), coords, 1)
+    holder.cmaps[holder.stride] = coords
+    for s, c, m in zip(h["strides"], h["coarse"], ns[1:]):
+        holder.cmaps[s] = c[:m]
+    prebuild_maps(holder)
+    return h["idx_query"], h["counts"][:ns[0]], coords, holder.cmaps, holder.kmaps
 
 
 # -------------------------------------------------------------------------------- voxelize
@@ -360,6 +438,55 @@ def prebuild_maps(x) -> int:
             kmap.flat_pairs
             kmap.dense_hint()
     return built
+
+
+class CoordPrefetch:
+    """Coordinate-only work of the NEXT scan batch (voxel keys, unique, coarse coordinate sets, kernel maps, tile sorts, pair
+    lists — everything that depends on coordinates alone) on a high-priority side stream, in two phases queued from the
+    training loop's own thread:
+        begin(fn)   before the current step is queued: fn() launches the counting kernels (no host wait); they run as soon
+                    as the previous step has finished on the GPU, next to the start of the current one;
+        finish(fn)  after the current step is queued: fn() reads the counts — long since there, the host is several ms
+                    ahead of the GPU by then — and queues the map builders, which run next to the step's tail.
+    The consumer's stream waits for the event finish() returns.  No worker thread (a Python thread that blocks in CUDA
+    calls while the main thread launches was measured at anything between +8 % and -45 %).
+
+    Memory: tensors allocated on the side stream are consumed on the main stream, which the caching allocator does not
+    track.  Results are therefore kept alive here for one more generation, and begin() orders the side stream behind the
+    main-stream position at that moment before it releases the older generation: the step that used it was queued before,
+    so a block can only be reused after its last reader."""
+
+    def __init__(self):
+        self.stream = None
+        self.keep = []
+
+    def _side(self):
+        main = torch.cuda.current_stream()
+        if self.stream is None or self.stream.device != main.device:
+            self.stream = torch.cuda.Stream(device=main.device, priority=-1)
+            self.keep = []
+        return main, self.stream
+
+    def begin(self, fn):
+        main, side = self._side()
+        mark = torch.cuda.Event()
+        mark.record(main)
+        side.wait_event(mark)        # inputs exist, and the steps that used older results are over ...
+        del self.keep[:-1]           # ... so those may go back to the side stream's pool (the newest is about to be used)
+        with torch.cuda.stream(side):
+            return fn()
+
+    def finish(self, fn):
+        _main, side = self._side()
+        with torch.cuda.stream(side):
+            out = fn()
+            done = torch.cuda.Event()
+            done.record(side)
+        self.keep.append(out)
+        return out, done
+
+
+coord_prefetch = CoordPrefetch()
 
 
 class KernelMap:
@@ -622,6 +749,75 @@ def _conv_gather_gemm(kind, kmap, x, w, w_transposed, table, n_dst, c_dst, math,
     return y if yadd is None else y.add_(yadd)
 
 
+class _WeightBlobs:
+    """bf16 weight blobs of every conv parameter seen so far, re-tiled together: the first conv that finds its parameter
+    changed (`_version` moved: an optimizer step, a state_dict load) re-tiles ALL registered parameters, both directions, in
+    one launch (u2_conv_pretile_run) instead of two small launches per layer and step (102 per SPVCNN step).  Blobs
+    persist; the job table is rebuilt only when the set of parameters (or one's storage) changes."""
+
+    def __init__(self):
+        self.entries = {}       # id(param) -> [weakref, data_ptr, shape, blob tensor, version, sbytes_fwd]
+        self.plan = None        # (device table, n_jobs, n_blocks)
+        self.enabled = True
+
+    def get(self, weight: torch.Tensor):
+        """(blob_fwd, blob_dgrad) for a [K, Cin, Cout] parameter; None when the arena is off."""
+        if not self.enabled:
+            return None
+        import weakref
+        e = self.entries.get(id(weight))
+        if e is None or e[0]() is not weight or e[1] != weight.data_ptr() or e[2] != tuple(weight.shape):
+            K, cin, cout = weight.shape
+            nb = K * cin * cout * 2
+            if len(self.entries) >= 4096:   # parameters that come and go (or fresh wrappers every call): not what this is for
+                self.entries = {k: v for k, v in self.entries.items() if v[0]() is not None}
+                if len(self.entries) >= 4096:
+                    self.enabled = False
+                    return None
+            e = [weakref.ref(weight), weight.data_ptr(), tuple(weight.shape),
+                 torch.empty(2 * nb, dtype=torch.uint8, device=weight.device), weight._version, nb]
+            self.entries[id(weight)] = e
+            self.plan = None                # joins the one-launch plan at the next change of the parameters
+            check(lib().u2_conv_pretile(weight.data_ptr(), K, cin, cout, MATH_BF16, e[3].data_ptr(), e[3].data_ptr() + nb, _st()))
+            _count(2)
+        elif e[4] != weight._version:
+            self._retile(weight.device)
+        return e[3][:e[5]], e[3][e[5]:]
+
+    def _retile(self, device):
+        import ctypes
+        import numpy as np
+        l = lib()
+        if self.plan is None or self.plan[3] != device:
+            live = {k: e for k, e in self.entries.items() if e[0]() is not None and e[3].device == device}
+            self.entries = {k: e for k, e in self.entries.items() if e[0]() is not None}
+            n = 2 * len(live)
+            W = np.zeros(n, np.uint64); B = np.zeros(n, np.uint64)
+            K = np.zeros(n, np.int32); Cs = np.zeros(n, np.int32); Cd = np.zeros(n, np.int32); T = np.zeros(n, np.int32)
+            for i, e in enumerate(live.values()):
+                k, cin, cout = e[2]
+                W[2 * i] = W[2 * i + 1] = e[1]
+                B[2 * i], B[2 * i + 1] = e[3].data_ptr(), e[3].data_ptr() + e[5]
+                K[2 * i] = K[2 * i + 1] = k
+                Cs[2 * i], Cd[2 * i], T[2 * i] = cin, cout, 0
+                Cs[2 * i + 1], Cd[2 * i + 1], T[2 * i + 1] = cout, cin, 1
+            host = np.zeros(max(l.u2_conv_pretile_plan_bytes(n), 1), np.uint8)
+            nblk = ctypes.c_int64(0)
+            check(l.u2_conv_pretile_plan(n, W.ctypes.data, B.ctypes.data, K.ctypes.data, Cs.ctypes.data, Cd.ctypes.data,
+                                         T.ctypes.data, MATH_BF16, host.ctypes.data, host.nbytes, ctypes.addressof(nblk)))
+            self.plan = (torch.from_numpy(host).to(device), n, int(nblk.value), device)
+        tab, n, nblk, _ = self.plan
+        check(l.u2_conv_pretile_run(tab.data_ptr(), n, nblk, _st()))
+        _count()
+        for e in self.entries.values():
+            w = e[0]()
+            if w is not None and e[3].device == device:
+                e[4] = w._version
+
+
+weight_blobs = _WeightBlobs()
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     """fp32 -> bf16 copy of a feature matrix (operand conversion of the bf16 conv mode)."""
     x = x.contiguous()
@@ -659,15 +855,18 @@ class ConvolutionFn(Function):
             assert feats.shape[0] == kmap.n_out, (feats.shape, kmap.sizes)
         m_fwd = _layer_math(math, cin, cout, K)
         x_op = bf16_view(feats) if m_fwd == MATH_BF16 else feats
-        out = _conv_gather_gemm("fwd", kmap, x_op, weight, False, table, n_dst, cout, m_fwd, side=bool(transposed))
+        arena = weight_blobs.get(weight) if (m_fwd == MATH_BF16 and isinstance(weight, torch.nn.Parameter) and
+                                             _layer_math(math, cout, cin, K) == MATH_BF16) else None
+        out = _conv_gather_gemm("fwd", kmap, x_op, weight, False, table, n_dst, cout, m_fwd, side=bool(transposed),
+                                blob=arena[0] if arena else None)
         # the bf16 copy (half the bytes) is what wgrad needs later; otherwise keep the fp32 rows
-        ctx.save_for_backward(x_op, weight)
+        ctx.save_for_backward(x_op, weight, arena[1] if arena else None)
         ctx.misc = (kmap, transposed, math, in_dtype)
         return out.to(in_dtype)
 
     @staticmethod
     def backward(ctx, grad_output):
-        x_op, weight = ctx.saved_tensors
+        x_op, weight, blob_dgrad = ctx.saved_tensors
         kmap, transposed, math, in_dtype = ctx.misc
         g = grad_output.contiguous().float()
         K, cin, cout = weight.shape
@@ -681,7 +880,8 @@ class ConvolutionFn(Function):
         if ctx.needs_input_grad[0]:
             bwd_table = kmap.nbr if transposed else kmap.nbrT
             grad_feats = _conv_gather_gemm("dgrad", kmap, g_bf16 if m_dgrad == MATH_BF16 else g, weight, True, bwd_table,
-                                           x_op.shape[0], cin, m_dgrad, side=not transposed).to(in_dtype)
+                                           x_op.shape[0], cin, m_dgrad, side=not transposed,
+                                           blob=blob_dgrad if m_dgrad == MATH_BF16 else None).to(in_dtype)
         if ctx.needs_input_grad[1]:
             if x_is_bf16 and m_wgrad != MATH_BF16:
                 x_op = x_op.float()  # (not reached for SPVCNN shapes: bf16 fwd implies bf16 wgrad)
@@ -971,9 +1171,15 @@ class ConvBNReLUFn(Function):
         # both weight blobs now (W[k] for this conv, W[k]^T for its dgrad): the parameter does not change before backward
         sbytes = l.u2_conv_scratch_bytes(n_dst, K, cin, cout, MATH_BF16)
         need_dgrad = ctx.needs_input_grad[0]
-        blobs = torch.empty(2 * sbytes if need_dgrad else sbytes, dtype=torch.uint8, device=dev)
-        check(l.u2_conv_pretile(weight.data_ptr(), K, cin, cout, MATH_BF16, blobs.data_ptr(),
-                                blobs.data_ptr() + sbytes if need_dgrad else None, st))
+        arena = weight_blobs.get(weight) if isinstance(weight, torch.nn.Parameter) else None
+        if arena is not None:
+            blobs, blob_dgrad = arena
+        else:
+            blobs = torch.empty(2 * sbytes if need_dgrad else sbytes, dtype=torch.uint8, device=dev)
+            check(l.u2_conv_pretile(weight.data_ptr(), K, cin, cout, MATH_BF16, blobs.data_ptr(),
+                                    blobs.data_ptr() + sbytes if need_dgrad else None, st))
+            blob_dgrad = blobs[sbytes:] if need_dgrad else None
+            _count(2 if need_dgrad else 1)
         if _state["sort_tiles"]:
             tab, perm, _ = kmap.sorted_tables(side)
             rows = ld
@@ -998,11 +1204,11 @@ class ConvBNReLUFn(Function):
                                  gamma.data_ptr(), beta.data_ptr(), int(relu), _ptr(residual), z.data_ptr(),
                                  zb.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * cout, _ptr(running_mean),
                                  _ptr(running_var), st))
-        _count(6)
+        _count(4)
         # with a residual the ReLU mask cannot be recomputed from y alone: keep the output z for it
         ctx.save_for_backward(feats_bf16, weight, y, gamma, beta, stats, sums,
                               z if (residual is not None and relu) else None,
-                              blobs[sbytes:] if need_dgrad else None)
+                              blob_dgrad if need_dgrad else None)
         ctx.misc = (kmap, transposed, relu, group, residual is not None)
         ctx.mark_non_differentiable(zb)
         ctx.set_materialize_grads(False)  # no zero-filled "gradient" for the bf16 copy / an unused alias
