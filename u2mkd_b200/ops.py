@@ -467,6 +467,10 @@ class CoordPrefetch:
             self.keep = []
         return main, self.stream
 
+    def reset(self):
+        """Forget the kept generations.  Only after a device synchronisation (nothing queued can still read them)."""
+        self.keep = []
+
     def begin(self, fn):
         main, side = self._side()
         mark = torch.cuda.Event()
