@@ -402,17 +402,19 @@ def run_ours(args, w):
     ops.conv_timer = None
     ops.set_overlap_rows(saved_overlap)
     clocks = sampler.stop() if rank == 0 else None
-    if os.environ.get("U2_BENCH_HOSTPROF") and rank == 0:
-        # where the host spends its time queueing a step (untimed extra pass; cProfile slows the host down ~2x)
+    if os.environ.get("U2_BENCH_HOSTPROF"):
+        # where the host spends its time queueing a step (untimed extra pass on EVERY rank — the step holds collectives —
+        # rank 0 writes its profile; cProfile slows the host down ~2x)
         import cProfile, pstats, io
         pr = cProfile.Profile()
         pr.enable()
         timed(args.steps, True)
         pr.disable()
-        buf = io.StringIO()
-        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
-        with open(os.environ["U2_BENCH_HOSTPROF"], "w") as fh:
-            fh.write(buf.getvalue())
+        if rank == 0:
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+            with open(os.environ["U2_BENCH_HOSTPROF"], "w") as fh:
+                fh.write(buf.getvalue())
     if args.quick:
         ms_e2e = ms
     else:
