@@ -278,8 +278,10 @@ def run_ours(args, w):
         from u2mkd_b200 import fusion
         fusion.optimize(net, fuse_conv_bn=not args.no_conv_bn, fuse_residual=not args.no_residual_fusion)  # same module tree / parameters; BN(+ReLU) run the fused kernels
     if world > 1:
+        # train_spformer.py:82-83.  With SyncBatchNorm every rank computes its running statistics from the same all-reduced
+        # sums (bitwise: the exchange adds in rank order), so DDP's per-step broadcast of ~190 buffers from rank 0 is redundant
         net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=args.bucket_mb)  # train_spformer.py:82-83
+                                                        bucket_cap_mb=args.bucket_mb, broadcast_buffers=bool(args.no_sync_bn))
         if args.grad_bf16:
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
             net.register_comm_hook(None, default_hooks.bf16_compress_hook)
