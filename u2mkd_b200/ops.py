@@ -448,8 +448,8 @@ class CoordPrefetch:
                     as the previous step has finished on the GPU, next to the start of the current one;
         finish(fn)  after the current step is queued: fn() reads the counts — long since there, the host is several ms
                     ahead of the GPU by then — and queues the map builders, which run next to the step's tail.
-    The consumer's stream waits for the event finish() returns.  No worker thread (a Python thread that blocks in CUDA
-    calls while the main thread launches was measured at anything between +8 % and -45 %).
+    The consumer's stream waits for the event finish() returns.  Neither phase blocks in steady state, so no worker thread
+    is needed (profiles/r2_prefetch_steplog.md).
 
     Memory: tensors allocated on the side stream are consumed on the main stream, which the caching allocator does not
     track.  Results are therefore kept alive here for one more generation, and begin() orders the side stream behind the
