@@ -8,7 +8,9 @@ torchpack.utils.config (the global `configs` mapping) — and the import path th
     from core.models.nuscenes.spvcnn_spformer import SPVCNN_SPFORMER      # reference file, unchanged
 
 A shim is only registered when the real package is NOT importable.  Trainer-level torchpack (Trainer, callbacks,
-distributed launch) is out of scope."""
+distributed, environ, logging, fs / io: torchpack_shim.py), prettytable, the one nuscenes-devkit class core/callbacks.py
+imports and visualize_utils (open3d) come with it, so that train_spformer.py's own classes — core.spformer_trainer.
+NuScenesTrainer, core.callbacks.MeanIoU — run unchanged; synthetic_nusc.py supplies the dataset they consume."""
 import importlib
 import importlib.util
 import sys
@@ -119,16 +121,74 @@ class Config(dict):
             self[k] = v
 
     def update(self, other=(), **kwargs):
+        """dict: merged key by key (nested dicts recursively).  list of command-line strings (train_spformer.py:33-34,
+        `configs.update(opts)`): `--a.b.c value` / `--a.b.c=value` pairs, values read as Python literals when they parse."""
+        if isinstance(other, (list, tuple)) and all(isinstance(o, str) for o in other):
+            self._update_from_args(list(other))
+            other = ()
         for k, v in dict(other, **kwargs).items():
             if isinstance(v, dict) and isinstance(self.get(k), Config):
                 self[k].update(v)
             else:
                 self[k] = v
 
+    def _update_from_args(self, opts):
+        import ast
+        i = 0
+        while i < len(opts):
+            opt = opts[i]
+            if not opt.startswith("--"):
+                raise ValueError(f"config override {opt!r}: expected --key[.subkey] value")
+            if "=" in opt:
+                key, raw = opt[2:].split("=", 1)
+                i += 1
+            else:
+                if i + 1 >= len(opts):
+                    raise ValueError(f"config override {opt!r} has no value")
+                key, raw = opt[2:], opts[i + 1]
+                i += 2
+            try:
+                value = ast.literal_eval(raw)
+            except (ValueError, SyntaxError):
+                value = {"true": True, "false": False, "none": None, "null": None}.get(raw.lower(), raw)
+            node = self
+            parts = key.split(".")
+            for part in parts[:-1]:
+                if not isinstance(node.get(part), Config):
+                    node[part] = Config()
+                node = node[part]
+            node[parts[-1]] = value
+
     def load(self, fpath, recursive=False):
+        """YAML file into this mapping.  recursive=True (train_spformer.py:32): first every `default.yaml` found on the way
+        from the top-most directory of the path down to the file's own directory, then the file itself."""
+        import os
         import yaml
-        with open(fpath) as f:
-            self.update(yaml.safe_load(f) or {})
+        if not os.path.exists(fpath):
+            raise FileNotFoundError(fpath)
+        fpaths = [fpath]
+        if recursive:
+            extension = os.path.splitext(fpath)[1]
+            d = fpath
+            while os.path.dirname(d) != d:
+                d = os.path.dirname(d)
+                fpaths.append(os.path.join(d, "default" + extension))
+            fpaths = [fp for fp in reversed(fpaths) if os.path.exists(fp)]
+        for fp in fpaths:
+            with open(fp) as f:
+                self.update(yaml.safe_load(f) or {})
+
+    def __str__(self):
+        def lines(node, indent):
+            out = []
+            for k, v in node.items():
+                if isinstance(v, dict):
+                    out.append(" " * indent + f"{k}:")
+                    out += lines(v, indent + 2)
+                else:
+                    out.append(" " * indent + f"{k}: {v}")
+            return out
+        return "\n".join(lines(self, 0))
 
 
 configs = Config()
@@ -164,10 +224,53 @@ def install_reference_shims() -> list:
         _module("torch_scatter", scatter_mean=scatter_mean, scatter_add=scatter_add, scatter_sum=scatter_sum, scatter_max=scatter_max)
         done.append("torch_scatter")
     if _missing("torchpack"):
+        from . import torchpack_shim as tp
         cfg = _module("torchpack.utils.config", Config=Config, configs=configs)
-        utils = _module("torchpack.utils", config=cfg)
-        _module("torchpack", utils=utils)
-        done.append("torchpack.utils.config")
+        log = _module("torchpack.utils.logging", logger=tp.logger)
+        typ = _module("torchpack.utils.typing", Dataset=torch.utils.data.Dataset, Optimizer=torch.optim.Optimizer,
+                      Scheduler=torch.optim.lr_scheduler.LRScheduler, Trainer=tp.Trainer)
+        fsm = _module("torchpack.utils.fs", **{k: getattr(tp.fs, k) for k in ("normpath", "makedir", "remove", "exists")})
+        iom = _module("torchpack.utils.io", save=tp.io.save, load=tp.io.load)
+        utils = _module("torchpack.utils", config=cfg, logging=log, typing=typ, fs=fsm, io=iom)
+        d = tp.distributed
+        dist = _module("torchpack.distributed", **{k: getattr(d, k) for k in (
+            "init", "size", "rank", "local_size", "local_rank", "is_master", "barrier", "allgather", "allreduce", "broadcast")})
+        env = _module("torchpack.environ", get_run_dir=tp.get_run_dir, set_run_dir=tp.set_run_dir, auto_set_run_dir=tp.auto_set_run_dir)
+        cb_names = ("Callback", "Callbacks", "LambdaCallback", "ProgressBar", "EstimatedTimeLeft", "InferenceRunner", "Saver",
+                    "MaxSaver", "MinSaver", "SummaryWriter", "ConsoleWriter", "TFEventWriter", "JSONLWriter", "MetaInfoSaver")
+        cbk = {k: getattr(tp, k) for k in cb_names}
+        cbmod = _module("torchpack.callbacks.callback", Callback=tp.Callback, Callbacks=tp.Callbacks, LambdaCallback=tp.LambdaCallback)
+        cbs = _module("torchpack.callbacks", callback=cbmod, **cbk)
+        cbs.__path__ = []   # `from torchpack.callbacks.callback import Callback` treats it as a package
+        summ = _module("torchpack.train.summary", Summary=tp.Summary)
+        exc = _module("torchpack.train.exception", StopTraining=tp.StopTraining)
+        train = _module("torchpack.train", Trainer=tp.Trainer, Summary=tp.Summary, StopTraining=tp.StopTraining, summary=summ,
+                        exception=exc)
+        train.__path__ = []
+        utils.__path__ = []
+        top = _module("torchpack", utils=utils, distributed=dist, environ=env, callbacks=cbs, train=train)
+        top.__path__ = []
+        done.append("torchpack")
+    if _missing("prettytable"):
+        from . import torchpack_shim as tp
+        _module("prettytable", PrettyTable=tp.PrettyTable)
+        done.append("prettytable")
+    if _missing("nuscenes"):
+        from . import torchpack_shim as tp
+        u = _module("nuscenes.eval.lidarseg.utils", ConfusionMatrix=tp.ConfusionMatrix)
+        ls = _module("nuscenes.eval.lidarseg", utils=u)
+        ev = _module("nuscenes.eval", lidarseg=ls)
+        top = _module("nuscenes", eval=ev)
+        for m in (ls, ev, top):
+            m.__path__ = []
+        done.append("nuscenes.eval.lidarseg.utils")
+    if _missing("open3d") and "visualize_utils" not in sys.modules:
+        # visualize_utils.py (repo root of the reference) needs open3d at import time; the trainers import two drawing helpers
+        # from it and never call them on the training path (core/spformer_trainer.py:17,67-73 — commented out)
+        def _no_display(*_a, **_k):
+            raise RuntimeError("visualize_utils: no display / open3d in this environment")
+        _module("visualize_utils", visualize_img=_no_display, visualize_pcd=_no_display)
+        done.append("visualize_utils")
     sptr = importlib.import_module("u2mkd_b200.sptr")
     # the import path the reference uses (spherical_transformer.py:7).  A real `third_party` package on sys.path (the
     # reference checkout) is left alone — only the `sptr` leaf, whose own __init__ would import the absent `sptr_cuda`
