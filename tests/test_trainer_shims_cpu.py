@@ -193,9 +193,63 @@ def test_unmodified_train_spformer_script_runs_through_the_launcher():
     scheduler, samplers, DataLoaders, NuScenesTrainer.train_with_defaults + InferenceRunner / MeanIoU / MaxSaver / Saver) via
     u2mkd_b200.shims.launch.run_script with the synthetic dataset; one epoch of the reference's own SPVCNN on CPU
     (tests/trainer_script_run.py)."""
-    r = subprocess.run([sys.executable, os.path.join(HERE, "trainer_script_run.py")], capture_output=True, text=True, timeout=850)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "trainer_script_run.py"), "spformer"], capture_output=True, text=True, timeout=850)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["checkpoints"] == ["max-iou-val-vox.pt", "step-2.pt"] and out["metainfo"] == ["args.txt", "configs.json"]
     row = out["rows"][-1]
     assert row["epoch_num"] == 1 and row["global_step"] == 2 and np.isfinite(row["total_loss"]) and 0 <= row["iou/val/vox"] <= 100
+
+
+@pytest.mark.timeout(1500)
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train_lc_nusc_tsd_full.py")), reason="reference tree not present (GPU box)")
+def test_unmodified_student_distillation_script_runs_through_the_launcher():
+    """train_lc_nusc_tsd_full.py (BASELINE configs[4]: the cross-modal teacher-student run) unchanged: the reference's own
+    SPVCNN_SWIFTNET18_SPFORMER_TSD_FULL (SwiftNet image branch, SphereFormer blocks, point<->pixel loops), its
+    NuScenesLCTSDFullTrainer (lovasz + KL + feature MSE, teacher logits mapped to the student's voxels through inverse_map ->
+    keyframe_mask_full -> inds) and three MeanIoU metrics, over the torchpack stand-in and the synthetic LiDAR + six-camera
+    dataset (student / teacher feed_dicts of lc_semantic_nusc_tsd_full.py:436-462).  One epoch on CPU."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "trainer_script_run.py"), "student"], capture_output=True, text=True, timeout=1400)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["checkpoints"] == ["max-iou-pix-val.pt", "max-iou-vox-val.pt", "step-2.pt"]
+    row = out["rows"][-1]
+    for k in ("ce/vox", "ce/pix", "ce/kl", "mse/feat", "mse/layer0", "mse/layer3", "total_loss"):
+        assert np.isfinite(row[k]), (k, row)
+    for k in ("iou-vox/val", "iou-pix/val", "iou-vox-t/val"):
+        assert 0 <= row[k] <= 100, (k, row)
+    assert row["epoch_num"] == 1 and row["global_step"] == 2
+
+
+def test_synthetic_camera_dataset_contract(oracle):
+    """feed_dict_s / feed_dict_t of lc_semantic_nusc_tsd_full.py:436-462: shapes, the camera masks, and the index chain the
+    distillation trainer relies on (teacher voxels -> all teacher points -> keyframe points -> the student's voxels)."""
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "torchsparse" or k.startswith("torchsparse.")}
+    oracle.install_as_torchsparse()
+    try:
+        from u2mkd_b200.shims.synthetic_nusc import SyntheticNuScenesCameras
+        ds = SyntheticNuScenesCameras(voxel_size=0.2, num_train=2, num_val=2, multisweeps=2, max_points=4000, image_size=(36, 64), im_drop=3)
+        tr, va = ds["train"][0], ds["val"][0]
+        assert set(tr) == {"feed_dict_s", "feed_dict_t", "lidar_token"}
+        s, t = va["feed_dict_s"], va["feed_dict_t"]
+        n = s["num_vox"]
+        assert s["images"].shape == (6, 36, 64, 3) and tr["feed_dict_s"]["images"].shape == (3, 36, 64, 3)      # im_drop on train
+        assert s["pixel_coordinates"].shape == (6, n, 2) and s["masks"].shape == (6, n) and s["masks"].dtype == bool
+        pc, m = s["pixel_coordinates"], s["masks"]
+        assert bool((np.abs(pc[m]) < 1).all()) and 0.2 < m.any(0).mean() <= 1.0
+        assert np.array_equal(s["fov_mask"].F, m.any(0)) and len(s["inds"]) == 1 and s["inds"][0].shape == (n,)
+        assert bool((s["label_fov"].F[s["label_fov"].F > 0] == s["targets_mapped"].F[s["label_fov"].F > 0]).all())
+        kf = t["keyframe_mask_full"].F
+        n_key = s["targets_mapped"].F.shape[0]
+        assert t["num_pts"] == kf.shape[0] and int(kf.sum()) == n_key and bool(kf[:n_key].all())              # keyframe first
+        # val split (no augmentation): teacher voxel features reach the student's voxels through the trainer's index chain
+        feats_t = t["lidar"].F[t["inverse_map"].F][kf][s["inds"][0]]
+        vs_t, vs_s = np.round(feats_t[:, :3] / 0.2), np.round(s["lidar"].F[:, :3] / 0.2)
+        assert np.array_equal(vs_t, vs_s)                                                                     # same voxel
+        batch = ds["val"].collate_fn([ds["val"][0], ds["val"][1]])
+        assert isinstance(batch["feed_dict_s"]["masks"], list) and batch["feed_dict_s"]["images"].shape[:2] == (2, 6)
+        assert batch["feed_dict_t"]["num_pts"] == [ds["val"][0]["feed_dict_t"]["num_pts"], ds["val"][1]["feed_dict_t"]["num_pts"]]
+    finally:
+        for k in [k for k in sys.modules if k == "torchsparse" or k.startswith("torchsparse.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})

@@ -18,7 +18,7 @@ import runpy
 import sys
 
 
-def _patch_dataset(n_train: int, n_val: int, max_points: int, force: bool) -> None:
+def _patch_dataset(n_train: int, n_val: int, max_points: int, force: bool, image_size=None) -> None:
     import importlib
     builder = importlib.import_module("core.builder")
     real = builder.make_dataset
@@ -30,19 +30,25 @@ def _patch_dataset(n_train: int, n_val: int, max_points: int, force: bool) -> No
         if not force and root and os.path.isdir(str(root)):
             return real(dataset_name, **kwargs)
         ds = configs.dataset
-        return SyntheticNuScenes(voxel_size=ds.voxel_size, num_train=n_train, num_val=n_val,
-                                 multisweeps=ds.get("multisweeps", {}).get("num_sweeps", 0),
-                                 num_classes=configs.data.num_classes, ignored_label=configs.data.get("ignore_label", 0),
-                                 seed=configs.get("train", {}).get("seed", 0) or 0, flip_aug=ds.get("flip_aug", True),
-                                 rotate_aug=ds.get("rotate_aug", True), translate_std=ds.get("translate_std", None),
-                                 max_points=max_points)
+        common = dict(voxel_size=ds.voxel_size, num_train=n_train, num_val=n_val,
+                      multisweeps=ds.get("multisweeps", {}).get("num_sweeps", 0), num_classes=configs.data.num_classes,
+                      ignored_label=configs.data.get("ignore_label", 0), seed=configs.get("train", {}).get("seed", 0) or 0,
+                      max_points=max_points)
+        name = dataset_name if dataset_name is not None else ds.name
+        if name == "lc_semantic_nusc_tsd_full":     # LiDAR + six cameras, student / teacher inputs
+            from .synthetic_nusc import SyntheticNuScenesCameras
+            size = image_size or [int(x * ds.get("im_cr", 0.4)) for x in (900, 1600)]
+            return SyntheticNuScenesCameras(image_size=size, im_drop=ds.get("im_drop", 0),
+                                            debug=configs.get("debug", {}).get("debug_val", True), **common)
+        return SyntheticNuScenes(flip_aug=ds.get("flip_aug", True), rotate_aug=ds.get("rotate_aug", True),
+                                 translate_std=ds.get("translate_std", None), **common)
 
     builder.make_dataset = make_dataset
 
 
 def run_script(script: str, argv, synthetic=None) -> None:
     """script: path of the reference script; argv: its own arguments; synthetic: None (real dataset unless its root is
-    missing) or (n_train, n_val, max_points)."""
+    missing) or (n_train, n_val, max_points[, image_h, image_w])."""
     import u2mkd_b200
     script = os.path.abspath(script)
     root = os.path.dirname(script)
@@ -51,8 +57,9 @@ def run_script(script: str, argv, synthetic=None) -> None:
     if "torchsparse" not in sys.modules:
         u2mkd_b200.install_as_torchsparse()
     u2mkd_b200.install_reference_shims()
-    n_train, n_val, max_points = synthetic if synthetic is not None else (64, 16, 0)
-    _patch_dataset(n_train, n_val, max_points, force=synthetic is not None)
+    n_train, n_val, max_points = (tuple(synthetic) + (0,))[:3] if synthetic is not None else (64, 16, 0)
+    image_size = tuple(synthetic[3:5]) if synthetic is not None and len(synthetic) >= 5 else None
+    _patch_dataset(n_train, n_val, max_points, force=synthetic is not None, image_size=image_size)
     sys.argv = [script] + list(argv)
     runpy.run_path(script, run_name="__main__")
 
@@ -62,7 +69,7 @@ def main() -> None:
     synthetic = None
     if args and args[0] == "--synthetic":
         parts = [int(v) for v in args[1].split(",")]
-        synthetic = (parts[0], parts[1] if len(parts) > 1 else max(1, parts[0] // 4), parts[2] if len(parts) > 2 else 0)
+        synthetic = (parts[0], parts[1] if len(parts) > 1 else max(1, parts[0] // 4), parts[2] if len(parts) > 2 else 0) + tuple(parts[3:5])
         args = args[2:]
     if not args:
         raise SystemExit(__doc__)
