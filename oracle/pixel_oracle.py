@@ -1,6 +1,7 @@
 """CPU oracle of the student's point <-> pixel transforms — TEST INFRASTRUCTURE.  The reference code IS plain torch, so the
-oracle is its statement-by-statement restatement (device-agnostic: `.cuda()` calls dropped), parity unpinned by stored
-vectors (the reference has none for this path) but identical in construction:
+oracle is its statement-by-statement restatement (device-agnostic: `.cuda()` calls dropped).  PINNED to the reference's own
+code: tests/test_pixel_oracle_pin_cpu.py runs core/models/fusion_blocks.py's Feature_Gather / Feature_Fetch and the unmodified
+student model's inline multi-scale loop (captured with forward hooks) on CPU next to these functions — difference exactly 0.
   Point2Grid      core/models/fusion_blocks.py:217-238
   Feature_Gather  core/models/fusion_blocks.py:241-254
   Feature_Fetch   core/models/fusion_blocks.py:257-278
