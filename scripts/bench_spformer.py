@@ -36,7 +36,8 @@ def main():
     ops.set_math("bf16")
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0)
-    net = models_spformer.product().SPVCNN_SPFORMER(**kw).cuda()
+    import copy   # the constructor scales the spherical sizes in place, like the reference's
+    net = models_spformer.product().SPVCNN_SPFORMER(**copy.deepcopy(kw)).cuda()
     fusion.optimize(net)
     opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4, fused=True)
     dev = [tuple(a.cuda() for a in b) for b in batches]
@@ -79,7 +80,7 @@ def main():
         torch.set_num_threads(os.cpu_count())
         fam = models.build_family(ts_oracle.as_torchsparse_modules()["torchsparse"])
         torch.manual_seed(0)
-        cnet = models_spformer.build_spformer_family(fam, sptr_oracle.as_sptr_module()).SPVCNN_SPFORMER(**kw)
+        cnet = models_spformer.build_spformer_family(fam, sptr_oracle.as_sptr_module()).SPVCNN_SPFORMER(**copy.deepcopy(kw))
         copt = torch.optim.SGD(cnet.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)
         c, f, t = batches[0]
         n1 = int((c[:, 3] == 0).sum())  # one scan of the batch

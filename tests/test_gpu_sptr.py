@@ -181,8 +181,9 @@ def test_spvcnn_spformer_model_against_oracle(cuda_lib, oracle):
               cr=1.0, num_classes=17)
     fam_o = models.build_family(oracle.as_torchsparse_modules()["torchsparse"])
     torch.manual_seed(0)
-    net_o = models_spformer.build_spformer_family(fam_o, sptr_oracle.as_sptr_module()).SPVCNN_SPFORMER(**kw)
-    net_g = models_spformer.product().SPVCNN_SPFORMER(**kw)
+    import copy   # the constructor scales the spherical sizes IN PLACE, like the reference's (spvcnn_spformer.py:80-83)
+    net_o = models_spformer.build_spformer_family(fam_o, sptr_oracle.as_sptr_module()).SPVCNN_SPFORMER(**copy.deepcopy(kw))
+    net_g = models_spformer.product().SPVCNN_SPFORMER(**copy.deepcopy(kw))
     net_g.load_state_dict(net_o.state_dict())
     net_g.cuda()
     net_o.dropout = net_g.dropout = torch.nn.Identity()

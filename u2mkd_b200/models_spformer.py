@@ -161,21 +161,30 @@ def build_spformer_family(fam, sptr) -> SimpleNamespace:
                      pres, vres, **kwargs):
             super().__init__(pres=pres, vres=vres, **kwargs)
             cs = [int(kwargs.get("cr", 1.0) * c) for c in (32, 32, 64, 128, 256, 256, 128, 96, 96)]
-            window_size, quant_size = np.array(window_size, dtype=np.float64), np.array(quant_size, dtype=np.float64)
-            window_size_sphere, quant_size_sphere = list(window_size_sphere), list(quant_size_sphere)
+            # spvcnn_spformer.py:51-83 statement by statement, on the caller's own objects and dtypes — this matters: the cubic
+            # sizes are REBOUND per stage (`x = x * s`, new arrays) while the spherical ones are updated IN PLACE
+            # (`x[0] = x[0] * s`), and sptr's to_3d_numpy copies a list but returns an ndarray as is.  With builder.make_model's
+            # arguments (core/builder.py:540-553: window_size_sphere a list, quant_size_sphere an ndarray) every block therefore
+            # ends up sharing ONE quant_size_sphere array holding the final, 16 x scaled values at forward time, while its
+            # table length was fixed from the value at construction.  Reproduced as is (pinned against the unmodified model
+            # files on CPU, tests/test_spformer_mirror_pin_cpu.py).
+            self.window_size, self.window_size_sphere = window_size, window_size_sphere
+            self.quant_size, self.quant_size_sphere = quant_size, quant_size_sphere
             dpr = [x.item() for x in torch.linspace(0, drop_path_rate, 7)]
             head_dim = 16
             self.transformer_blocks = nn.ModuleList()
             for idx in range(1, 5):
                 self.transformer_blocks.append(SphereFormer(
-                    cs[idx], cs[idx] // head_dim, window_size.copy(), list(window_size_sphere), quant_size.copy(),
-                    list(quant_size_sphere), indice_key='sphereformer{}'.format(idx + 1), rel_query=True, rel_key=True,
+                    cs[idx], cs[idx] // head_dim, self.window_size, self.window_size_sphere, self.quant_size,
+                    self.quant_size_sphere, indice_key='sphereformer{}'.format(idx + 1), rel_query=True, rel_key=True,
                     rel_value=True, drop_path=dpr[idx], a=a))
                 sc, ss = window_size_scale
-                window_size, quant_size = window_size * sc, quant_size * sc
-                for j in (0, 1):
-                    window_size_sphere[j] *= ss
-                    quant_size_sphere[j] *= ss
+                self.window_size = self.window_size * sc
+                self.quant_size = self.quant_size * sc
+                self.window_size_sphere[0] = self.window_size_sphere[0] * ss
+                self.window_size_sphere[1] = self.window_size_sphere[1] * ss
+                self.quant_size_sphere[0] = self.quant_size_sphere[0] * ss
+                self.quant_size_sphere[1] = self.quant_size_sphere[1] * ss
             for m in self.modules():
                 if isinstance(m, nn.BatchNorm1d):
                     nn.init.constant_(m.weight, 1)
