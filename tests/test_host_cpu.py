@@ -242,3 +242,41 @@ def test_batch_norm_fallback_counts_batches_and_honours_momentum_none():
             assert torch.allclose(ya, yb, atol=1e-6)
         assert int(b.num_batches_tracked) == 3
         assert torch.allclose(a.running_mean, b.running_mean, atol=1e-6) and torch.allclose(a.running_var, b.running_var, atol=1e-5)
+
+
+def test_prefetch_host_logic_plan_strides_and_no_reference_cycle():
+    """Host side of the coordinate prefetch (ops.planned_strides, models.PreparedScan): the coarse strides come from the strided
+    convs of the recorded plan only, and a prepared batch must not form a reference cycle with its input tensor — a cycle
+    leaves the release of device memory to the cyclic collector (profiles/r2_prefetch_steplog.md)."""
+    import gc
+    import weakref
+    from u2mkd_b200 import ops
+    from u2mkd_b200.models import PreparedScan
+    saved = dict(ops._plan)
+    try:
+        ops._plan.clear()
+        one, two, three = (1, 1, 1), (2, 2, 2), (3, 3, 3)
+        ops._plan[(one, three, one, one)] = set()                 # submanifold k3: no new coordinate set
+        ops._plan[(one, two, two, one)] = {"sortF"}               # k2 s2: stride 1 -> 2
+        ops._plan[(two, three, one, one)] = set()
+        ops._plan[(two, two, two, one)] = set()                   # stride 2 -> 4
+        ops._plan[((4, 4, 4), three, two, one)] = set()           # k3 s2: not the {1, kernel_size} case, stays lazy
+        assert ops.planned_strides() == [two, (4, 4, 4)]
+    finally:
+        ops._plan.clear()
+        ops._plan.update(saved)
+
+    class X:      # stands in for the input SparseTensor
+        pass
+    gc.collect()
+    gc.disable()
+    try:
+        x = X()
+        prep = PreparedScan(x=x, src=None, res=(0.1, 0.1), done=None)
+        x._u2_prep = weakref.ref(prep)                            # what models.prepare_scan_finish stores
+        assert x._u2_prep() is prep
+        probe = weakref.ref(x)
+        del prep, x
+        assert probe() is None                                    # freed by reference counting alone, collector off
+    finally:
+        gc.enable()
