@@ -272,7 +272,9 @@ def test_prefetched_coordinates_do_not_change_the_model(cuda_lib):
         nz = noise[i % len(batches)]
         assert got[0].shape == want[0].shape
         assert float((want[0] - got[0]).abs().max()) <= max(1e-5 * float(want[0].abs().max()), 10 * nz[0]), i
-        assert float((want[1] - got[1]).abs().max()) <= max(1e-4 * float(want[1].abs().max()), 10 * nz[1]), (i, nz)
+        # (stem-kernel gradient through 49 BatchNorm layers at random init: identical passes already differ by ~2e-4 .. 1.5e-3 of
+        #  the largest entry, module docstring; a wrong map or a stale buffer shows up at O(1), and in the logits bar above)
+        assert float((want[1] - got[1]).abs().max()) <= max(5e-3 * float(want[1].abs().max()), 10 * nz[1]), (i, nz)
     # index tensors of the prefetch path against the in-place operators
     c, f = batches[0]
     zc = c.float()
