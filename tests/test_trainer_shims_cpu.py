@@ -191,8 +191,8 @@ def test_config_recursive_load_and_command_line_overrides(tmp_path):
 def test_unmodified_train_spformer_script_runs_through_the_launcher():
     """train_spformer.py itself (argument parsing, recursive configs + overrides, builder.make_model / criterion / optimizer /
     scheduler, samplers, DataLoaders, NuScenesTrainer.train_with_defaults + InferenceRunner / MeanIoU / MaxSaver / Saver) via
-    u2mkd_b200.shims.launch.run_script with the synthetic dataset; one epoch of the reference's own SPVCNN on CPU
-    (tests/trainer_script_run.py)."""
+    u2mkd_b200.shims.launch.run_script with the synthetic dataset and configs/nuscenes/train/spformer.yaml as is apart from sizes:
+    one epoch of the reference's own SPVCNN_SPFORMER with its lovasz criterion on CPU (tests/trainer_script_run.py)."""
     r = subprocess.run([sys.executable, os.path.join(HERE, "trainer_script_run.py"), "spformer"], capture_output=True, text=True, timeout=850)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])

@@ -3,7 +3,8 @@ through u2mkd_b200.shims.launch.run_script — argument parsing, recursive YAML 
 builder.make_* (dataset patched to the synthetic adapter; model / criterion / optimizer / scheduler the reference's own),
 samplers and DataLoaders, the reference's Trainer subclass under train_with_defaults with InferenceRunner / MeanIoU / MaxSaver /
 Saver.
-    argv[1] = "spformer": train_spformer.py (LiDAR only; the reference's core/models/semantickitti/spvcnn.py)
+    argv[1] = "spformer": train_spformer.py with configs/nuscenes/train/spformer.yaml as is, sizes aside (LiDAR only; the reference's
+                          SPVCNN_SPFORMER, lovasz criterion, sgd + cosine warm-up schedule)
     argv[1] = "student" : train_lc_nusc_tsd_full.py (teacher-student distillation, LiDAR + six synthetic cameras; the
                           reference's SPVCNN_SWIFTNET18_SPFORMER_TSD_FULL with its SwiftNet image branch, SphereFormer blocks,
                           point<->pixel loops and NuScenesLCTSDFullTrainer)
@@ -45,8 +46,8 @@ common = ["--run-dir", run_dir, "--non-dist", "--dataset.voxel_size", "0.4", "--
 if which == "spformer":
     launch.run_script(os.path.join(REF, "train_spformer.py"),
                       ["configs/nuscenes/train/spformer.yaml"] + common +
-                      ["--model.name", "spvcnn", "--model.cr", "0.25", "--criterion.name", "cross_entropy"],
-                      synthetic=(4, 2, 5000))
+                      [],   # the config's own model (spvcnn_spformer, cr 1.0) and criterion (lovasz + cross entropy)
+                      synthetic=(4, 2, 4000))
 else:
     launch.run_script(os.path.join(REF, "train_lc_nusc_tsd_full.py"),
                       ["configs/nuscenes/train/spformer_tsd_full_ours_star.yaml"] + common +
